@@ -1,0 +1,350 @@
+// ref_driver.cpp -- drives the UNMODIFIED reference classes (HashTable,
+// LPHashTable, ScanStructure, DataChunk, NaiveCompactor) with explicit inputs.
+//
+// TEST / BASELINE INFRASTRUCTURE ONLY.  This file contains no reference code:
+// it #includes the reference headers from /root/reference and is linked with
+// the reference's own base.cpp / chaining_ht.cpp / linear_probing_ht.cpp /
+// compactor.cpp, compiled where they lie (recipe: oracle/Makefile, outputs in
+// oracle/_ref/).  It exists because the reference's two drivers cannot be
+// used as-is: simd_micro_bench.cpp has UB in ParseParameters
+// (:35-73, missing return) and main.cpp discards results
+// (setting.h:31 flag_collect_tuples=false) and takes no input arrays.
+//
+// Sub-commands (all print one JSON line on stdout):
+//   main  J cf lhs rhs block compact [dump.bin]
+//         == main.cpp:37-115 with std::mt19937 gen(2) LHS, chaining table;
+//         compact: 0 none, 1 NaiveCompactor (built with the compactor.cpp:36 fix)
+//   pipe  lhs.bin rows J cf rhs block kind compact [dump.bin]
+//         same pipeline over an explicit row-major int64 LHS file; kind 0 LP, 1 chain
+//   nextdump kind n cf block keys.bin nkeys inone out.bin
+//         per-Next golden records of the chunk-granular protocol
+//   micro kind variant n cf block keys.bin nkeys procs
+//         times one micro-bench variant (simd_micro_bench.cpp:83-361 loop shape)
+//         variant: 0 scalar Probe+Next, 1 SIMD Probe+Next, 2 scalar InOneNext, 3 SIMD InOneNext
+//         procs > 1 forks that many workers over disjoint key ranges sharing the
+//         read-only table (the reference itself is single-threaded; its
+//         CycleProfiler singleton is not thread-safe, profiler.h:262-290)
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+
+#include "base.h"
+#include "chaining_ht.h"
+#include "compactor.h"
+#include "hash_functions.h"
+#include "linear_probing_ht.h"
+
+using namespace simd_compaction;
+
+namespace {
+
+struct Collector {
+  uint64_t n = 0, digest = 0;
+  std::vector<uint64_t> colsum;
+  std::vector<int64_t> tuples;
+  bool keep = false;
+  void Add(DataChunk &chunk) {  // same access pattern as data_collection.cpp:10-21
+    size_t nc = chunk.data_.size();
+    if (colsum.size() < nc) colsum.resize(nc, 0);
+    for (size_t i = 0; i < chunk.count_; ++i) {
+      auto idx = chunk.selection_vector_[i];
+      uint64_t th = 0x9e3779b97f4a7c15ULL;
+      for (size_t j = 0; j < nc; ++j) {
+        uint64_t v = (uint64_t) chunk.data_[j].GetValue(idx);
+        th = murmurhash64(th ^ v) + j;
+        colsum[j] += v;
+        if (keep) tuples.push_back((int64_t) v);
+      }
+      digest += th;
+      ++n;
+    }
+  }
+};
+
+template <class HT>
+struct Pipe {
+  std::vector<std::unique_ptr<HT>> hts;
+  std::vector<std::unique_ptr<DataChunk>> intermediates;
+  std::vector<std::unique_ptr<NaiveCompactor>> compactors;
+  Collector out;
+  bool compact = false;
+  uint64_t probe_tuples = 0, next_calls = 0;
+  std::vector<uint64_t> level_in, level_chunks;
+
+  void Execute(DataChunk &input, size_t level) {  // protocol of main.cpp:119-170
+    if (level == hts.size()) {
+      out.Add(input);
+      return;
+    }
+    level_in[level] += input.count_;
+    level_chunks[level] += 1;
+    probe_tuples += input.count_;
+    auto &join_key = input.data_[level];
+    auto &result = intermediates[level];
+    auto ss = hts[level]->Probe(join_key, input.count_, input.selection_vector_);
+    while (ss.HasNext()) {
+      ++next_calls;
+      ss.Next(join_key, input, *result);
+      if (compact) {
+        compactors[level]->Compact(result);
+        if (result->count_ == 0) continue;
+      }
+      Execute(*result, level + 1);
+    }
+  }
+  void Flush(size_t level) {  // main.cpp:172-191
+    if (level == hts.size()) return;
+    compactors[level]->Flush(intermediates[level]);
+    Execute(*intermediates[level], level + 1);
+    Flush(level + 1);
+  }
+};
+
+std::vector<int64_t> ReadFile(const char *path, size_t n) {
+  std::vector<int64_t> v(n);
+  FILE *f = fopen(path, "rb");
+  if (!f || fread(v.data(), 8, n, f) != n) {
+    fprintf(stderr, "cannot read %zu int64 from %s\n", n, path);
+    exit(2);
+  }
+  fclose(f);
+  return v;
+}
+
+template <class HT>
+int RunPipe(const std::vector<int64_t> &lhs, size_t rows, size_t J, size_t cf, size_t rhs, bool compact,
+            const char *dump) {
+  std::vector<AttributeType> types(J, AttributeType::INTEGER);
+  Pipe<HT> p;
+  p.compact = compact;
+  p.out.keep = dump != nullptr;
+  p.level_in.assign(J, 0);
+  p.level_chunks.assign(J, 0);
+  for (size_t i = 0; i < J; ++i) {  // main.cpp:62-68
+    p.hts.push_back(std::make_unique<HT>(rhs, cf));
+    types.push_back(AttributeType::INTEGER);
+    types.push_back(AttributeType::INTEGER);
+    p.intermediates.push_back(std::make_unique<DataChunk>(types));
+    p.compactors.push_back(std::make_unique<NaiveCompactor>(types));
+  }
+  std::vector<AttributeType> in_types(J, AttributeType::INTEGER);
+  std::vector<Attribute> tuple(J);
+  auto t0 = std::chrono::steady_clock::now();
+  double secs = 0;
+  size_t start = 0, end;
+  do {  // main.cpp:81-95
+    end = std::min(start + kBlockSize, rows);
+    DataChunk chunk(in_types);
+    for (size_t i = start; i < end; ++i) {
+      for (size_t j = 0; j < J; ++j) tuple[j] = lhs[i * J + j];
+      chunk.AppendTuple(tuple);
+    }
+    start = end;
+    t0 = std::chrono::steady_clock::now();
+    p.Execute(chunk, 0);
+    secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  } while (end < rows);
+  if (compact) {
+    t0 = std::chrono::steady_clock::now();
+    p.Flush(0);
+    secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  printf("{\"n_tuples\": %llu, \"digest\": %llu, \"probe_tuples\": %llu, \"next_calls\": %llu, \"seconds\": %.6f, \"colsum\": [",
+         (unsigned long long) p.out.n, (unsigned long long) p.out.digest, (unsigned long long) p.probe_tuples,
+         (unsigned long long) p.next_calls, secs);
+  for (size_t j = 0; j < 3 * J; ++j)
+    printf("%s%llu", j ? ", " : "", (unsigned long long) (j < p.out.colsum.size() ? p.out.colsum[j] : 0));
+  printf("], \"level_in\": [");
+  for (size_t j = 0; j < J; ++j) printf("%s%llu", j ? ", " : "", (unsigned long long) p.level_in[j]);
+  printf("], \"level_chunks\": [");
+  for (size_t j = 0; j < J; ++j) printf("%s%llu", j ? ", " : "", (unsigned long long) p.level_chunks[j]);
+  printf("]}\n");
+  if (dump) {
+    FILE *f = fopen(dump, "wb");
+    fwrite(p.out.tuples.data(), 8, p.out.tuples.size(), f);
+    fclose(f);
+  }
+  return 0;
+}
+
+// per-Next records: u32 count, then count x (u32 physical position, i64 payload at that position)
+template <class HT>
+int NextDump(size_t n, size_t cf, const std::vector<int64_t> &keys, bool inone, const char *out) {
+  HT table(n, cf);
+  std::vector<uint32_t> sel(kBlockSize);
+  for (uint32_t i = 0; i < kBlockSize; ++i) sel[i] = i;
+  DataChunk input(std::vector<AttributeType>{AttributeType::INTEGER});
+  DataChunk output(std::vector<AttributeType>{AttributeType::INTEGER, AttributeType::INTEGER, AttributeType::INTEGER});
+  Vector block(AttributeType::INTEGER);
+  FILE *f = fopen(out, "wb");
+  uint64_t n_tuples = 0, n_calls = 0;
+  for (size_t k = 0; k < keys.size(); k += kBlockSize) {
+    size_t fill = std::min(kBlockSize, keys.size() - k);
+    for (size_t i = 0; i < fill; ++i) block.GetValue(i) = keys[k + i];
+    input.data_[0] = block;
+    input.count_ = fill;
+    auto ss = table.Probe(block, fill, sel);
+    while (ss.HasNext()) {
+      size_t rc = inone ? ss.InOneNext(block, input, output) : ss.Next(block, input, output);
+      uint32_t c32 = (uint32_t) rc;
+      fwrite(&c32, 4, 1, f);
+      for (size_t i = 0; i < rc; ++i) {
+        uint32_t pos = output.selection_vector_[i];
+        int64_t payload = output.data_[2].GetValue(pos);
+        fwrite(&pos, 4, 1, f);
+        fwrite(&payload, 8, 1, f);
+      }
+      n_tuples += rc;
+      ++n_calls;
+    }
+    uint32_t end_marker = 0xFFFFFFFFu;  // end of this input chunk
+    fwrite(&end_marker, 4, 1, f);
+  }
+  fclose(f);
+  printf("{\"n_tuples\": %llu, \"next_calls\": %llu}\n", (unsigned long long) n_tuples, (unsigned long long) n_calls);
+  return 0;
+}
+
+template <class HT>
+uint64_t MicroLoop(HT &table, const int64_t *keys, size_t nkeys, int variant) {
+  std::vector<uint32_t> sel(kBlockSize);
+  for (uint32_t i = 0; i < kBlockSize; ++i) sel[i] = i;
+  DataChunk input(std::vector<AttributeType>{AttributeType::INTEGER});
+  DataChunk output(std::vector<AttributeType>{AttributeType::INTEGER, AttributeType::INTEGER, AttributeType::INTEGER});
+  Vector block(AttributeType::INTEGER);
+  uint64_t n_tuples = 0;
+  for (size_t k = 0; k < nkeys; k += kBlockSize) {
+    size_t fill = std::min(kBlockSize, nkeys - k);
+    for (size_t i = 0; i < fill; ++i) block.GetValue(i) = keys[k + i];
+    input.data_[0] = block;
+    input.count_ = fill;
+    switch (variant) {
+      case 0: {
+        auto ss = table.Probe(block, fill, sel);
+        while (ss.HasNext()) n_tuples += ss.Next(block, input, output);
+        break;
+      }
+      case 1: {
+        auto ss = table.SIMDProbe(block, fill, sel);
+        while (ss.HasNext()) n_tuples += ss.SIMDNext(block, input, output);
+        break;
+      }
+      case 2: {
+        auto ss = table.Probe(block, fill, sel);
+        while (ss.HasNext()) n_tuples += ss.InOneNext(block, input, output);
+        break;
+      }
+      default: {
+        auto ss = table.SIMDProbe(block, fill, sel);
+        while (ss.HasNext()) n_tuples += ss.SIMDInOneNext(block, input, output);
+        break;
+      }
+    }
+  }
+  return n_tuples;
+}
+
+template <class HT>
+int Micro(size_t n, size_t cf, const std::vector<int64_t> &keys, int variant, int procs) {
+  auto b0 = std::chrono::steady_clock::now();
+  HT table(n, cf);
+  double build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+  uint64_t total = 0;
+  double secs = 0;
+  if (procs <= 1) {
+    auto t0 = std::chrono::steady_clock::now();
+    total = MicroLoop(table, keys.data(), keys.size(), variant);
+    secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  } else {
+    std::vector<int> fds(procs);
+    std::vector<pid_t> pids(procs);
+    size_t per = (keys.size() / procs / kBlockSize) * kBlockSize;
+    if (per == 0) per = keys.size();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int p = 0; p < procs; ++p) {
+      int fd[2];
+      if (pipe(fd)) return 3;
+      pid_t pid = fork();
+      if (pid == 0) {
+        close(fd[0]);
+        size_t lo = std::min(keys.size(), (size_t) p * per);
+        size_t hi = p == procs - 1 ? keys.size() : std::min(keys.size(), lo + per);
+        uint64_t r = MicroLoop(table, keys.data() + lo, hi - lo, variant);
+        if (write(fd[1], &r, 8) != 8) _exit(4);
+        _exit(0);
+      }
+      close(fd[1]);
+      fds[p] = fd[0];
+      pids[p] = pid;
+    }
+    for (int p = 0; p < procs; ++p) {
+      uint64_t r = 0;
+      if (read(fds[p], &r, 8) != 8) return 5;
+      total += r;
+      close(fds[p]);
+      int st;
+      waitpid(pids[p], &st, 0);
+    }
+    secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  printf("{\"n_tuples\": %llu, \"seconds\": %.6f, \"build_seconds\": %.3f, \"probe_keys\": %zu, \"procs\": %d, \"variant\": %d}\n",
+         (unsigned long long) total, secs, build_s, keys.size(), procs > 1 ? procs : 1, variant);
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: ref_driver main|pipe|nextdump|micro ...\n");
+    return 1;
+  }
+  std::string cmd = argv[1];
+  if (cmd == "main" && argc >= 8) {
+    size_t J = atol(argv[2]), cf = atol(argv[3]), lhs_n = atol(argv[4]), rhs = atol(argv[5]);
+    kBlockSize = atol(argv[6]);
+    bool compact = atoi(argv[7]) != 0;
+    kJoins = J;
+    std::mt19937 gen(2);  // main.cpp:41-43
+    std::uniform_int_distribution<> dist(0, rhs);
+    std::vector<int64_t> lhs(lhs_n * J);
+    for (size_t i = 0; i < lhs_n; ++i)
+      for (size_t j = 0; j < J; ++j) lhs[i * J + j] = size_t(dist(gen));
+    return RunPipe<HashTable>(lhs, lhs_n, J, cf, rhs, compact, argc > 8 ? argv[8] : nullptr);
+  }
+  if (cmd == "pipe" && argc >= 10) {
+    size_t rows = atol(argv[3]), J = atol(argv[4]), cf = atol(argv[5]), rhs = atol(argv[6]);
+    kBlockSize = atol(argv[7]);
+    int kind = atoi(argv[8]);
+    bool compact = atoi(argv[9]) != 0;
+    kJoins = J;
+    auto lhs = ReadFile(argv[2], rows * J);
+    const char *dump = argc > 10 ? argv[10] : nullptr;
+    return kind == 0 ? RunPipe<LPHashTable>(lhs, rows, J, cf, rhs, compact, dump)
+                     : RunPipe<HashTable>(lhs, rows, J, cf, rhs, compact, dump);
+  }
+  if (cmd == "nextdump" && argc >= 10) {
+    int kind = atoi(argv[2]);
+    size_t n = atol(argv[3]), cf = atol(argv[4]);
+    kBlockSize = atol(argv[5]);
+    auto keys = ReadFile(argv[6], atol(argv[7]));
+    bool inone = atoi(argv[8]) != 0;
+    return kind == 0 ? NextDump<LPHashTable>(n, cf, keys, inone, argv[9]) : NextDump<HashTable>(n, cf, keys, inone, argv[9]);
+  }
+  if (cmd == "micro" && argc >= 10) {
+    int kind = atoi(argv[2]), variant = atoi(argv[3]);
+    size_t n = atol(argv[4]), cf = atol(argv[5]);
+    kBlockSize = atol(argv[6]);
+    auto keys = ReadFile(argv[7], atol(argv[8]));
+    int procs = atoi(argv[9]);
+    return kind == 0 ? Micro<LPHashTable>(n, cf, keys, variant, procs) : Micro<HashTable>(n, cf, keys, variant, procs);
+  }
+  fprintf(stderr, "bad arguments\n");
+  return 1;
+}
