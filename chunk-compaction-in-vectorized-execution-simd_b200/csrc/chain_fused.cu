@@ -1,0 +1,368 @@
+// chain_fused.cu -- a whole chain of hash joins in ONE persistent kernel with
+// in-kernel chunk compaction between the joins.
+//
+// Reference protocol (main.cpp:119-191):
+//   ExecutePipeline(chunk, L): ss = hts[L]->Probe(...); while (ss.HasNext()) {
+//       ss.Next(...); compactors[L]->Compact(result); if (result->count_ == 0) continue;
+//       ExecutePipeline(result, L + 1); }            -- depth first, one live chunk per level
+//   FlushPipelineCache: drain every compactor top-down at the end.
+//
+// GPU form: a CTA is one pipeline instance.  All per-level operator state lives in
+// shared memory, so nothing between two joins ever touches HBM:
+//   * scan[L]   = the ScanStructure of level L: (row, pos, end) for kW lanes
+//   * chunk[L]  = the Compactor cache in front of level L: up to (kS+1)*kW LHS row ids
+// A CTA-uniform state machine replays the reference's recursion iteratively:
+//   - if chunk[cur+1] holds >= threshold rows -> Probe the next join with them (descend)
+//   - else if scan[cur] still has lanes        -> one round (Next) at level cur
+//   - else                                     -> return to the parent level (ascend)
+//   - at the top: pull the next kW-row LHS chunk; when the table is exhausted, flush
+//     the caches top-down (FlushPipelineCache).
+// A round lets every active lane inspect up to kS consecutive chain entries / slots
+// (one 32-byte sector), ranks the matches with a block-wide exclusive scan and appends
+// the matching rows DENSELY to chunk[cur+1] -- the compaction step (K3/K10/K11 of
+// SURVEY 2.1).  With threshold == kW downstream joins only ever see full chunks
+// (NaiveCompactor); threshold == 0 pushes every Next result down as is (no compaction).
+//
+// In the reference's key-only tables the payload of a match IS the probe key
+// (chaining_ht.cpp:34 drops the payload column), so an intermediate row is fully
+// described by its LHS row id; the result tuple [k_0..k_{J-1}, 0,k_0, 0,k_1, ...]
+//  is rebuilt from the LHS columns at the ResultCollector.
+#include "common.cuh"
+
+namespace ccb {
+
+constexpr int kW = CC_CHAIN_WIDTH;  // chunk width == threads per CTA
+constexpr int kS = 4;               // entries inspected per lane per round (one sector)
+constexpr int kBufCap = (kS + 1) * kW;
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+constexpr int kWarps = kW / 32;
+
+struct ChainLevel {
+  const uint64_t *slots;
+  const uint2 *dir;
+  const int64_t *ckeys;
+  uint64_t mask;
+  const int64_t *col;  // LHS join-key column of this level
+  uint32_t need;       // rows that must be cached before the next join runs (1..kW)
+  int kind;
+  int unique;
+};
+
+struct ChainArgs {
+  ChainLevel lv[CC_MAX_JOINS];
+  int64_t *out[3 * CC_MAX_JOINS];
+  int n_joins;
+  int materialize;
+  size_t n_rows;
+  size_t cap;
+  cc_chain_result *res;
+};
+
+struct ChainShared {
+  unsigned long long cs[CC_MAX_JOINS];
+  unsigned long long digest;
+  unsigned long long base;
+  unsigned long long level_in[CC_MAX_JOINS], steps[CC_MAX_JOINS], lanes[CC_MAX_JOINS];
+  unsigned long long tile;
+  uint32_t bufcnt[CC_MAX_JOINS + 1];
+  uint32_t active[CC_MAX_JOINS];
+  uint32_t scan[33];
+};
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t &total, uint32_t *s_w) {
+  uint32_t incl = warp_incl_scan_u32(v);
+  unsigned w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_w[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = lane_id() < kWarps ? s_w[lane_id()] : 0;
+    uint32_t xi = warp_incl_scan_u32(x);
+    s_w[lane_id()] = xi - x;
+    if (lane_id() == 31) s_w[32] = xi;
+  }
+  __syncthreads();
+  uint32_t off = s_w[w] + incl - v;
+  total = s_w[32];
+  __syncthreads();
+  return off;
+}
+
+__global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChainShared &S = *reinterpret_cast<ChainShared *>(smem_raw);
+  uint32_t *st_row = reinterpret_cast<uint32_t *>(smem_raw + sizeof(ChainShared));
+  uint32_t *st_pos = st_row + a.n_joins * kW;
+  uint32_t *st_end = st_pos + a.n_joins * kW;
+  uint32_t *bufs = st_end + a.n_joins * kW;  // chunk[L] for L = 1 .. J-1 at bufs + (L-1)*kBufCap
+  const int J = a.n_joins;
+  const unsigned tid = threadIdx.x;
+
+  if (tid == 0) {
+    for (int j = 0; j < CC_MAX_JOINS; ++j) S.cs[j] = S.level_in[j] = S.steps[j] = S.lanes[j] = 0, S.active[j] = 0;
+    for (int j = 0; j <= CC_MAX_JOINS; ++j) S.bufcnt[j] = 0;
+    S.digest = 0;
+    atomicMin((unsigned long long *) &a.res->reserved[1], (unsigned long long) globaltimer_ns());
+  }
+  __syncthreads();
+
+  const size_t ntiles = (a.n_rows + kW - 1) / kW;
+  int cur = -1;
+  bool exhausted = false;
+
+  // Probe (chaining_ht.cpp:38-58 / linear_probing_ht.cpp:39-60) for the rows handed to level L
+  auto start_scan = [&](int L, uint32_t row) {
+    const ChainLevel &lv = a.lv[L];
+    bool act = false;
+    uint32_t pos = 0, end = 0;
+    if (row != kNoRow) {
+      uint64_t key = (uint64_t) __ldg(lv.col + row);
+      uint64_t h = murmurhash64(key) & lv.mask;
+      if (lv.kind == CC_HT_CHAIN) {
+        uint2 d = __ldg(lv.dir + h);
+        pos = d.x;
+        end = d.x + d.y;
+        act = d.y != 0;
+      } else {
+        pos = (uint32_t) h;
+        act = ld_nc_u64(lv.slots + h) != kEmptyU;
+      }
+    }
+    st_row[L * kW + tid] = act ? row : kNoRow;
+    st_pos[L * kW + tid] = pos;
+    st_end[L * kW + tid] = end;
+    int n_valid = __syncthreads_count(row != kNoRow);
+    int n_act = __syncthreads_count(act);
+    if (tid == 0) {
+      S.active[L] = (uint32_t) n_act;
+      S.level_in[L] += (unsigned long long) n_valid;
+    }
+    __syncthreads();
+  };
+
+  for (;;) {
+    if (cur < 0) {
+      uint32_t row = kNoRow;
+      int L = 0;
+      if (!exhausted) {
+        if (tid == 0) S.tile = atomicAdd((unsigned long long *) &a.res->reserved[0], 1ull);
+        __syncthreads();
+        size_t tile = (size_t) S.tile;
+        __syncthreads();
+        if (tile < ntiles) {
+          size_t r = tile * (size_t) kW + tid;
+          row = r < a.n_rows ? (uint32_t) r : kNoRow;
+        } else {
+          exhausted = true;
+        }
+      }
+      if (exhausted) {
+        // FlushPipelineCache (main.cpp:172-191): drain the shallowest non-empty cache
+        L = 0;
+        for (int l = 1; l < J; ++l)
+          if (S.bufcnt[l] > 0) {
+            L = l;
+            break;
+          }
+        if (L == 0) break;  // every cache is empty: done
+        uint32_t cnt = S.bufcnt[L];
+        uint32_t take = cnt < (uint32_t) kW ? cnt : (uint32_t) kW;
+        row = tid < take ? bufs[(L - 1) * kBufCap + (cnt - take) + tid] : kNoRow;
+        __syncthreads();
+        if (tid == 0) S.bufcnt[L] = cnt - take;
+      }
+      start_scan(L, row);
+      cur = L;
+      continue;
+    }
+    // ---- descend: the compactor in front of level cur+1 has a chunk ready
+    if (cur + 1 < J) {
+      uint32_t cnt = S.bufcnt[cur + 1];
+      if (cnt >= a.lv[cur].need) {
+        uint32_t take = cnt < (uint32_t) kW ? cnt : (uint32_t) kW;
+        uint32_t row = tid < take ? bufs[cur * kBufCap + (cnt - take) + tid] : kNoRow;
+        __syncthreads();
+        if (tid == 0) S.bufcnt[cur + 1] = cnt - take;
+        start_scan(cur + 1, row);
+        ++cur;
+        continue;
+      }
+    }
+    // ---- ascend: this level's scan is exhausted (HasNext() == false)
+    if (S.active[cur] == 0) {
+      --cur;
+      continue;
+    }
+    // ---- one round (Next) at level cur
+    {
+      const int L = cur;
+      const ChainLevel &lv = a.lv[L];
+      uint32_t row = st_row[L * kW + tid];
+      uint32_t m = 0;
+      bool still = false;
+      uint64_t key = 0;
+      if (row != kNoRow) {
+        key = (uint64_t) __ldg(lv.col + row);
+        uint32_t p = st_pos[L * kW + tid];
+        if (lv.kind == CC_HT_CHAIN) {
+          uint32_t e = st_end[L * kW + tid];
+          uint64_t v[kS];
+#pragma unroll
+          for (int s = 0; s < kS; ++s) v[s] = (p + s < e) ? (uint64_t) __ldg(lv.ckeys + p + s) : ~key;
+#pragma unroll
+          for (int s = 0; s < kS; ++s) m += (p + s < e) && (v[s] == key);
+          p = (e - p > (uint32_t) kS) ? p + kS : e;
+          still = p != e;
+        } else {
+          uint64_t v[kS];
+#pragma unroll
+          for (int s = 0; s < kS; ++s) v[s] = ld_nc_u64(lv.slots + ((uint64_t) (p + s) & lv.mask));
+          still = true;
+#pragma unroll
+          for (int s = 0; s < kS; ++s) {
+            if (still) {
+              if (v[s] == kEmptyU)
+                still = false;  // walk ends at the first empty slot (linear_probing_ht.cpp:104-108)
+              else
+                m += (v[s] == key);
+            }
+          }
+          p = (uint32_t) ((uint64_t) (p + kS) & lv.mask);
+        }
+        if (lv.unique && m) still = false;
+        st_pos[L * kW + tid] = p;
+        if (!still) st_row[L * kW + tid] = kNoRow;
+      }
+      int n_lanes = __syncthreads_count(row != kNoRow);
+      uint32_t total;
+      uint32_t off = block_excl_scan(m, total, S.scan);
+      if (L + 1 < J) {
+        // Compact: append the matching rows densely to the next level's cached chunk
+        uint32_t cnt0 = S.bufcnt[L + 1];
+        uint32_t *dst = bufs + L * kBufCap + cnt0 + off;
+        for (uint32_t q = 0; q < m; ++q) dst[q] = row;
+        __syncthreads();
+        if (tid == 0) S.bufcnt[L + 1] = cnt0 + total;
+      } else if (total) {
+        // ResultCollector (main.cpp:125-128, data_collection.cpp:10-21)
+        if (tid == 0) S.base = atomicAdd((unsigned long long *) &a.res->n_tuples, (unsigned long long) total);
+        uint64_t th = 0;
+        if (m) {
+          th = 0x9e3779b97f4a7c15ULL;
+          for (int j = 0; j < 3 * J; ++j) {
+            uint64_t v = j < J ? (uint64_t) __ldg(a.lv[j].col + row) : (((j - J) & 1) ? (uint64_t) __ldg(a.lv[(j - J) >> 1].col + row) : 0ull);
+            th = murmurhash64(th ^ v) + (uint64_t) j;
+          }
+          th *= (uint64_t) m;
+        }
+        th = warp_sum_u64(th);
+        if (lane_id() == 0 && th) atomicAdd(&S.digest, (unsigned long long) th);
+        for (int j = 0; j < J; ++j) {
+          uint64_t v = m ? (uint64_t) __ldg(a.lv[j].col + row) * (uint64_t) m : 0ull;
+          v = warp_sum_u64(v);
+          if (lane_id() == 0 && v) atomicAdd(&S.cs[j], (unsigned long long) v);
+        }
+        __syncthreads();
+        if (a.materialize && m) {
+          uint64_t base = S.base + off;
+          for (int j = 0; j < 3 * J; ++j) {
+            int64_t v = j < J ? __ldg(a.lv[j].col + row) : (((j - J) & 1) ? __ldg(a.lv[(j - J) >> 1].col + row) : 0ll);
+            for (uint32_t q = 0; q < m; ++q)
+              if (base + q < a.cap) a.out[j][base + q] = v;
+          }
+        }
+      }
+      int n_still = __syncthreads_count(still);
+      if (tid == 0) {
+        S.active[L] = (uint32_t) n_still;
+        S.steps[L] += 1;
+        S.lanes[L] += (unsigned long long) n_lanes;
+      }
+      __syncthreads();
+    }
+  }
+
+  __syncthreads();
+  if (tid < (unsigned) J) {
+    unsigned long long v = S.cs[tid];
+    if (v) {
+      atomicAdd((unsigned long long *) &a.res->colsum[tid], v);
+      atomicAdd((unsigned long long *) &a.res->colsum[J + 2 * tid + 1], v);
+    }
+    atomicAdd((unsigned long long *) &a.res->level_in[tid], S.level_in[tid]);
+    atomicAdd((unsigned long long *) &a.res->level_steps[tid], S.steps[tid]);
+    atomicAdd((unsigned long long *) &a.res->level_lanes[tid], S.lanes[tid]);
+  }
+  if (tid == 0) {
+    if (S.digest) atomicAdd((unsigned long long *) &a.res->digest, S.digest);
+    atomicMax((unsigned long long *) &a.res->reserved[2], (unsigned long long) globaltimer_ns());
+  }
+}
+
+__global__ void chain_finish_kernel(cc_chain_result *res, size_t cap, int materialize) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    res->overflow = (materialize && res->n_tuples > cap) ? 1 : 0;
+    res->device_ns = res->reserved[2] >= res->reserved[1] ? res->reserved[2] - res->reserved[1] : 0;
+  }
+}
+
+__global__ void chain_init_kernel(cc_chain_result *res) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) res->reserved[1] = ~0ull;
+}
+
+}  // namespace ccb
+
+using namespace ccb;
+
+extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
+                                const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
+                                cc_chain_result *d_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(h_tables && h_lhs_cols && d_result, "NULL argument");
+  CC_REQUIRE(n_joins >= 1 && n_joins <= CC_MAX_JOINS, "n_joins must be in [1, %d]", CC_MAX_JOINS);
+  CC_REQUIRE(n_rows < 0xFFFFFFFFull, "at most 2^32-2 LHS rows per call (got %zu)", n_rows);
+  cudaStream_t st = as_stream(s);
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_joins = (int) n_joins;
+  a.n_rows = n_rows;
+  a.res = d_result;
+  a.materialize = h_out_cols != nullptr;
+  a.cap = a.materialize ? out_capacity : 0;
+  for (size_t l = 0; l < n_joins; ++l) {
+    const cc_ht *t = h_tables[l];
+    CC_REQUIRE(t && h_lhs_cols[l], "NULL table or column at level %zu", l);
+    CC_REQUIRE(t->n_slots <= (1ull << 32), "table at level %zu has more than 2^32 slots", l);
+    ChainLevel &lv = a.lv[l];
+    lv.slots = t->d_slots;
+    lv.dir = t->d_dir;
+    lv.ckeys = t->d_ckeys;
+    lv.mask = t->mask;
+    lv.col = h_lhs_cols[l];
+    lv.kind = t->kind;
+    lv.unique = !t->has_duplicates;
+    uint32_t thr = thresholds ? thresholds[l] : (uint32_t) kW;
+    lv.need = thr < 1 ? 1u : (thr > (uint32_t) kW ? (uint32_t) kW : thr);
+  }
+  if (a.materialize)
+    for (size_t j = 0; j < 3 * n_joins; ++j) {
+      CC_REQUIRE(h_out_cols[j], "NULL output column %zu", j);
+      a.out[j] = h_out_cols[j];
+    }
+  CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_chain_result), st));
+  chain_init_kernel<<<1, 32, 0, st>>>(d_result);
+  CC_CHECK_LAUNCH();
+  if (n_rows) {
+    size_t smem = sizeof(ChainShared) + n_joins * 3 * kW * sizeof(uint32_t) + (n_joins - 1) * (size_t) kBufCap * sizeof(uint32_t);
+    CC_CUDA(cudaFuncSetAttribute(chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int per_sm = 0;
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_fused_kernel, kW, smem));
+    if (per_sm < 1) per_sm = 1;
+    size_t ntiles = (n_rows + kW - 1) / kW;
+    size_t grid = std::min<size_t>(ntiles, (size_t) sm_count() * per_sm);
+    chain_fused_kernel<<<(unsigned) grid, kW, smem, st>>>(a);
+    CC_CHECK_LAUNCH();
+  }
+  chain_finish_kernel<<<1, 32, 0, st>>>(d_result, a.cap, a.materialize);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}

@@ -1,0 +1,282 @@
+/*
+ * cc_api.h -- C ABI of the B200-native hash-join probe + chunk-compaction
+ * engine (libccb200.so).
+ *
+ * The reference (YimingQiao/Chunk-Compaction-in-Vectorized-Execution-SIMD) has
+ * no FFI / plugin surface: its boundary is the C++ class surface that main.cpp
+ * and simd_micro_bench.cpp call.  Every entry point below names
+ * the reference interface (file:line in the reference tree) it replaces; the
+ * C++ facade in  chunk-compaction-in-vectorized-execution-simd_b200/host/
+ * simd_compaction.hpp  re-creates those classes on top of this ABI.
+ *
+ * Conventions
+ *   - plain C, opaque handles, no CUDA/torch types in signatures
+ *     (cc_stream_t is a cudaStream_t carried as void*; NULL = default stream)
+ *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are host
+ *   - every function returns CC_OK (0) or a negative cc_status; the message
+ *     of the last failure on the calling thread is cc_last_error()
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with CC_ERR_NO_DEVICE
+ *   - all arithmetic is integer and bit-exact w.r.t. the reference; the only
+ *     floating point is the bandit's double maths (negative_feedback.hpp)
+ */
+#ifndef CC_API_H
+#define CC_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_API_VERSION 1
+
+typedef enum {
+  CC_OK = 0,
+  CC_ERR_INVALID = -1,     /* bad argument                                   */
+  CC_ERR_NO_DEVICE = -2,   /* no CUDA device / not sm_100                    */
+  CC_ERR_CUDA = -3,        /* CUDA runtime error (see cc_last_error)         */
+  CC_ERR_NOMEM = -4,       /* device or host allocation failed               */
+  CC_ERR_CAPACITY = -5,    /* output buffer too small (required size stored) */
+  CC_ERR_UNSUPPORTED = -6, /* e.g. key -1 in an LP table (empty sentinel)    */
+  CC_ERR_STATE = -7        /* call sequence violation (e.g. Next after end)  */
+} cc_status;
+
+typedef void *cc_stream_t; /* cudaStream_t */
+
+typedef struct cc_ht cc_ht;               /* HashTable / LPHashTable            */
+typedef struct cc_scan cc_scan;           /* ScanStructure / LPScanStructure    */
+typedef struct cc_compactor cc_compactor; /* NaiveCompactor (+Binary/Dynamic)   */
+typedef struct cc_tuner cc_tuner;         /* CompactTuner                       */
+typedef struct cc_chain cc_chain;         /* PipelineState (main.cpp:14-20)     */
+
+/* table kinds */
+#define CC_HT_LP 0    /* linear_probing_ht.h:56 LPHashTable */
+#define CC_HT_CHAIN 1 /* chaining_ht.h:86 HashTable         */
+
+/* build flags */
+#define CC_BUILD_ORDERED 0   /* default: deterministic layout == serial insertion in ascending (unsigned) key
+                                order (LP) / insertion order (chain); equals the reference's layout for its
+                                own generator (keys are non-decreasing, chaining_ht.cpp:17-26)               */
+#define CC_BUILD_UNORDERED 1 /* plain CAS inserts, layout depends on scheduling (same multiset)              */
+
+/* ------------------------------------------------------------------ runtime */
+int cc_api_version(void);
+const char *cc_last_error(void);
+
+typedef struct {
+  int device;
+  int sm_major, sm_minor;
+  int sm_count;
+  size_t l2_bytes;
+  size_t total_mem, free_mem;
+  char name[128];
+} cc_device_info;
+
+int cc_device_init(int device); /* cudaSetDevice + capability check (must be sm_100) */
+int cc_device_get_info(cc_device_info *info);
+
+/* thin memory/stream helpers so C / C++ hosts need no CUDA headers */
+int cc_malloc(void **d_ptr, size_t bytes);
+int cc_free(void *d_ptr);
+int cc_host_alloc(void **h_ptr, size_t bytes); /* pinned */
+int cc_host_free(void *h_ptr);
+int cc_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, cc_stream_t stream);
+int cc_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, cc_stream_t stream);
+int cc_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, cc_stream_t stream);
+int cc_memset(void *d_dst, int byte, size_t bytes, cc_stream_t stream);
+int cc_stream_create(cc_stream_t *stream);
+int cc_stream_destroy(cc_stream_t stream);
+int cc_stream_sync(cc_stream_t stream);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t cc_launch_count(void);
+
+/* ------------------------------------------------------------ hash function */
+/* hash_functions.h:8-16 murmurhash64 (K1: mm512_murmurhash64 :18-28)          */
+int cc_hash_u64(const uint64_t *d_in, uint64_t *d_out, size_t n, cc_stream_t stream);
+
+/* --------------------------------------------------------------- generators */
+/* build keys: chaining_ht.cpp:15-26 == linear_probing_ht.cpp:14-25           */
+int cc_gen_build_keys(int64_t *d_keys, size_t n, size_t chunk_factor, cc_stream_t stream);
+/* SURVEY 8d C4/C5 probe keys: d_keys[i] = murmurhash64(seed + first + i) & mask */
+int cc_gen_keys_counter(int64_t *d_keys, size_t n, uint64_t seed, uint64_t first, uint64_t mask, cc_stream_t stream);
+
+/* -------------------------------------------------------------- hash tables */
+typedef struct {
+  int kind;
+  size_t n_keys;
+  size_t n_slots;    /* LP: slots (pow2 >= 4n); chain: buckets (pow2 >= 2n)            */
+  size_t bytes;      /* device bytes held                                              */
+  int has_duplicates; /* some key occurs more than once (probe must walk past matches) */
+  size_t max_chain;  /* chain: longest bucket; LP: 0                                   */
+} cc_ht_info;
+
+/* LPHashTable::LPHashTable (linear_probing_ht.cpp:4-37) / HashTable::HashTable
+ * (chaining_ht.cpp:4-36) over caller-supplied keys (the reference generates its
+ * own keys; see cc_ht_build_reference).  Key -1 is rejected for LP tables
+ * (empty-slot sentinel, linear_probing_ht.cpp:7).                             */
+int cc_ht_build(cc_ht **ht, int kind, const int64_t *d_keys, size_t n, int flags, cc_stream_t stream);
+/* exact equivalent of `HashTable(n_rhs_tuples, chunk_factor)` /
+ * `LPHashTable(n_rhs_tuples, chunk_factor)` (chaining_ht.h:88, linear_probing_ht.h:58) */
+int cc_ht_build_reference(cc_ht **ht, int kind, size_t n_rhs_tuples, size_t chunk_factor, cc_stream_t stream);
+/* import a host-built LP slot array (interop with a CPU engine; n_slots must be pow2) */
+int cc_ht_import_lp(cc_ht **ht, const int64_t *h_slots, size_t n_slots, size_t n_keys, cc_stream_t stream);
+int cc_ht_get_info(const cc_ht *ht, cc_ht_info *info);
+/* export for tests: LP -> slots[n_slots]; chain -> begin[n_buckets] u32, count[n_buckets] u32, keys[n_keys] */
+int cc_ht_export_lp(const cc_ht *ht, int64_t *h_slots);
+int cc_ht_export_chain(const cc_ht *ht, uint32_t *h_begin, uint32_t *h_count, int64_t *h_keys);
+int cc_ht_destroy(cc_ht *ht);
+
+/* ------------------------------------------- chunk-granular probe protocol */
+/* HashTable::Probe (chaining_ht.cpp:38-58) / LPHashTable::Probe
+ * (linear_probing_ht.cpp:39-60): d_key_col[block] column storage, d_sel[block]
+ * selection vector, count active rows.  The scan object keeps a reference to
+ * d_sel for chain tables (chaining_ht.h:54) and a private copy for LP tables
+ * (linear_probing_ht.h:48).                                                   */
+int cc_probe_chunk(const cc_ht *ht, const int64_t *d_key_col, size_t count, const uint32_t *d_sel, size_t block_size,
+                   cc_scan **scan, cc_stream_t stream);
+/* ScanStructure::HasNext (chaining_ht.h:48) / LPScanStructure::HasNext (:42)  */
+int cc_scan_has_next(const cc_scan *scan);
+size_t cc_scan_active(const cc_scan *scan);
+/* ScanStructure::Next (chaining_ht.cpp:60-80) / LPScanStructure::Next
+ * (linear_probing_ht.cpp:62-115).  in_one != 0 selects InOneNext
+ * (chaining_ht.cpp:138-173 / linear_probing_ht.cpp:117-153).
+ *   d_in_sel      input.selection_vector_ (Slice composes through it, base.cpp:42-46)
+ *   d_out_sel     result.selection_vector_[block]: first *out_count entries are the
+ *                 composed physical positions, the rest identity (Reset, base.h:96-99)
+ *   d_out_payload result.data_[ncol_in + 1] column storage [block]: payload written at
+ *                 the physical LHS position (chaining_ht.cpp:132)
+ * Synchronous (returns the count like the reference).                         */
+int cc_scan_next(cc_scan *scan, int in_one, const int64_t *d_key_col, const uint32_t *d_in_sel, uint32_t *d_out_sel,
+                 int64_t *d_out_payload, size_t *out_count, cc_stream_t stream);
+int cc_scan_destroy(cc_scan *scan);
+
+/* DataChunk::Append (base.cpp:15-27): for each of ncol columns
+ *   dst[c][dst_count + j] = src[c][src_sel[offset + j]],  j < num.
+ * d_dst_cols / d_src_cols are HOST arrays of ncol device column pointers.     */
+int cc_chunk_append(int64_t *const *h_dst_cols, size_t dst_count, const int64_t *const *h_src_cols,
+                    const uint32_t *d_src_sel, size_t num, size_t offset, size_t ncol, cc_stream_t stream);
+/* DataChunk::Slice selection composition (base.cpp:42-46, SIMDSlice :49-68):
+ *   d_out_sel[i] = d_other_sel[d_sv[i]], i < count                            */
+int cc_sel_compose(uint32_t *d_out_sel, const uint32_t *d_other_sel, const uint32_t *d_sv, size_t count,
+                   cc_stream_t stream);
+/* DataChunk::Reset (base.h:96-99): identity selection vector                  */
+int cc_sel_identity(uint32_t *d_sel, size_t block_size, cc_stream_t stream);
+/* DataCollection::FetchChunk (data_collection.cpp:23-27) row-major -> columnar
+ * and AppendChunk (:10-21) columnar+sel -> row-major, on device.               */
+int cc_rows_to_columns(const int64_t *d_rows, size_t n_rows, size_t ncol, int64_t *const *h_cols, cc_stream_t stream);
+int cc_columns_to_rows(const int64_t *const *h_cols, const uint32_t *d_sel, size_t count, size_t ncol, int64_t *d_rows,
+                       cc_stream_t stream);
+
+/* ------------------------------------------------------ batch probe (fast) */
+/* One launch probes a whole key column and writes DENSE (compacted) output
+ * columns -- the fused equivalent of the micro-bench loop
+ * simd_micro_bench.cpp:83-116 (Probe + while(HasNext) Next) followed by a
+ * Compactor on every result chunk.
+ *   d_out_key[i], d_out_payload[i] : probe key and matched build key of result
+ *       row i (reference result tuple [k, 0, k], SURVEY 8c layout); either may
+ *       be NULL (count / checksum only)
+ *   d_out_rowid[i] (optional, may be NULL): index of the probe row
+ *   out_capacity : rows the output columns can hold
+ *   d_result     : device cc_probe_result, written by the kernel
+ * Row order in the output is unspecified (multiset semantics).                */
+typedef struct {
+  uint64_t n_matches;   /* result rows (== #tuples of the micro-bench)             */
+  uint64_t key_sum;     /* wrapping sum of probe keys over result rows             */
+  uint64_t payload_sum; /* wrapping sum of payloads over result rows               */
+  uint64_t overflow;    /* != 0: out_capacity was too small, rows beyond were cut  */
+} cc_probe_result;
+
+int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
+                   uint64_t *d_out_rowid, size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
+/* host-buffer convenience (the end-to-end path bench.py times as `e2e`): copies h_keys to
+ * the device in slices, probes, copies the dense result columns back.          */
+int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_t *h_out_key, int64_t *h_out_payload,
+                        size_t out_capacity, cc_probe_result *h_result, cc_stream_t stream);
+
+/* -------------------------------------------------------------- compactor */
+/* NaiveCompactor (compactor.h:14-29, compactor.cpp:5-41), result-transparent
+ * (deep copies; SURVEY 8c bug 3), plus the Binary/Dynamic threshold of
+ * setting.h:21,24 / main.cpp:141,166:  count >= threshold passes through.
+ * threshold == block_size  <=> NaiveCompactor.                                */
+int cc_compactor_create(cc_compactor **c, size_t ncol, size_t block_size, size_t threshold);
+int cc_compactor_set_threshold(cc_compactor *c, size_t threshold); /* main.cpp:141 SetThreshold */
+size_t cc_compactor_get_threshold(const cc_compactor *c);          /* main.cpp:166 GetThreshold */
+/* Compact(unique_ptr<DataChunk>&): in: chunk columns h_cols[ncol] (device ptrs), d_sel, *count.
+ * out: *count == 0 (buffered)  or  the chunk to push downstream: h_out_cols[ncol] receive the
+ * device column pointers of the emitted chunk (the compactor's own dense storage, valid until
+ * the next Compact/Flush), *d_out_sel its selection vector, *count its row count.
+ * A pass-through returns the caller's own pointers.                            */
+int cc_compactor_compact(cc_compactor *c, int64_t *const *h_cols, const uint32_t *d_sel, size_t *count,
+                         int64_t **h_out_cols, const uint32_t **d_out_sel, cc_stream_t stream);
+/* Flush (compactor.h:23): hands out the partial cache.                        */
+int cc_compactor_flush(cc_compactor *c, int64_t **h_out_cols, const uint32_t **d_out_sel, size_t *count,
+                       cc_stream_t stream);
+int cc_compactor_destroy(cc_compactor *c);
+
+/* ------------------------------------------------------ fused join chain */
+/* ExecutePipeline + FlushPipelineCache (main.cpp:119-191) for a whole LHS table
+ * in ONE persistent kernel: every CTA pulls 2048-row chunks, probes level 0,
+ * compacts matches into a shared-memory chunk, runs level 1 on it once it holds
+ * >= thresholds[0] rows, and so on (depth-first, like the reference recursion).
+ *   h_tables[n_joins]        one table per level
+ *   h_lhs_cols[n_joins]      device column pointers of the LHS table (columnar)
+ *   thresholds[n_joins]      thresholds[L] = compaction threshold of the compactor that sits
+ *                            after join L (main.cpp:155): 0 = no compaction (every Next result
+ *                            is pushed downstream as is) .. >= CC_CHAIN_WIDTH = full compaction;
+ *                            NULL = full compaction everywhere
+ *   d_out_cols (optional)    HOST array of 3*n_joins device column pointers receiving the
+ *                            materialised result tuples [k_0..k_{J-1}, 0,k_0, 0,k_1, ...]
+ *                            (DataCollection::AppendChunk, data_collection.cpp:10-21);
+ *                            NULL = count + checksums only (flag_collect_tuples=false, setting.h:31) */
+#define CC_CHAIN_WIDTH 512
+#define CC_MAX_JOINS 8
+typedef struct {
+  uint64_t n_tuples;                /* rows reaching the ResultCollector                      */
+  uint64_t digest;                  /* SURVEY 8c digest                                       */
+  uint64_t colsum[3 * CC_MAX_JOINS]; /* per-column wrapping sums                               */
+  uint64_t level_in[CC_MAX_JOINS];  /* rows entering each level's probe                       */
+  uint64_t level_steps[CC_MAX_JOINS]; /* CTA-wide probe steps executed per level ("chunks")    */
+  uint64_t level_lanes[CC_MAX_JOINS]; /* sum of active lanes over those steps (density)        */
+  uint64_t overflow;
+  uint64_t device_ns;               /* device-side duration (globaltimer ns), bandit reward   */
+  uint64_t reserved[3];             /* kernel-internal cursors (chunk cursor, first/last timestamp) */
+} cc_chain_result;
+
+int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
+                     const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
+                     cc_chain_result *d_result, cc_stream_t stream);
+
+/* ------------------------------------------------------ compaction policy */
+/* CompactTuner (negative_feedback.hpp:165-260) with one MultiArmedBandit
+ * (:20-163) per join; FP64 arithmetic identical to the reference.            */
+int cc_tuner_create(cc_tuner **t);
+/* Initialize(address, arms = {0,32,64,128,256,384,512,768,1024}) (:172-177); arms NULL => default */
+int cc_tuner_initialize(cc_tuner *t, size_t address, const size_t *arms, size_t n_arms);
+int cc_tuner_select_arm(cc_tuner *t, size_t id, size_t *arm_value);        /* SelectArm  (:180-186) */
+int cc_tuner_update_arm(cc_tuner *t, size_t id, size_t arm_value, double reward); /* UpdateArm (:189-195) */
+int64_t cc_tuner_get_id(const cc_tuner *t, size_t address);                /* GetId      (:222-229) */
+size_t cc_tuner_bandit_size(const cc_tuner *t);                            /* GetBanditSize (:231)  */
+/* introspection for tests: est_rewards[n_arms], n_select[n_arms] of bandit id */
+int cc_tuner_state(const cc_tuner *t, size_t id, double *est_rewards, uint64_t *n_select, size_t n_arms);
+/* Reset(enable_log) (:197-220): dumps history CSVs under dir when enable_log, clears bandits */
+int cc_tuner_reset(cc_tuner *t, int enable_log, const char *log_dir);
+int cc_tuner_destroy(cc_tuner *t);
+
+/* ------------------------------------------------------------ multi-GPU */
+/* Hash partitioning for the partitioned join (new functionality):
+ * partition id = murmurhash64(key) >> (64 - log2 P).  Two-pass, deterministic:
+ *   cc_partition_count  : d_counts[P] = rows per partition
+ *   cc_partition_scatter: writes keys grouped by partition into d_out (P contiguous
+ *                         segments at d_offsets[p]); optional row ids alongside.
+ * The exchange itself (NCCL all-to-all over NVLink) is done by the host layer
+ * on these buffers.                                                           */
+int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t *d_counts, cc_stream_t stream);
+int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_offsets,
+                         uint64_t *d_cursors, int64_t *d_out, cc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CC_API_H */

@@ -24,6 +24,9 @@
 //         procs > 1 forks that many workers over disjoint key ranges sharing the
 //         read-only table (the reference itself is single-threaded; its
 //         CycleProfiler singleton is not thread-safe, profiler.h:262-290)
+//   bandit steps
+//         drives the reference CompactTuner / MultiArmedBandit (negative_feedback.hpp) with a
+//         deterministic synthetic reward stream and prints every selected threshold
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -39,6 +42,7 @@
 #include "compactor.h"
 #include "hash_functions.h"
 #include "linear_probing_ht.h"
+#include "negative_feedback.hpp"
 
 using namespace simd_compaction;
 
@@ -344,6 +348,26 @@ int main(int argc, char **argv) {
     auto keys = ReadFile(argv[7], atol(argv[8]));
     int procs = atoi(argv[9]);
     return kind == 0 ? Micro<LPHashTable>(n, cf, keys, variant, procs) : Micro<HashTable>(n, cf, keys, variant, procs);
+  }
+  if (cmd == "bandit" && argc >= 3) {
+    size_t steps = atol(argv[2]);
+    auto &tuner = CompactTuner::Get();
+    tuner.Initialize(0x1234);
+    uint64_t lcg = 88172645463325252ULL;
+    printf("{\"arms\": [");
+    for (size_t i = 0; i < steps; ++i) {
+      size_t thr = tuner.SelectArm(0);
+      // synthetic reward: best threshold 256 in the first half, 768 in the second (forces a drift restart)
+      lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+      double noise = double((lcg >> 33) % 1000) / 1000.0;
+      double best = i < steps / 2 ? 256.0 : 768.0;
+      double scale = i < steps / 2 ? 1.0 : 4.0;
+      double reward = scale * (2.0 - std::fabs(double(thr) - best) / 1024.0) + 0.05 * noise;
+      tuner.UpdateArm(0, thr, reward);
+      printf("%s%zu", i ? ", " : "", thr);
+    }
+    printf("]}\n");
+    return 0;
   }
   fprintf(stderr, "bad arguments\n");
   return 1;
