@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- probe tuples/sec of the B200 hash-join probe + compaction path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workloads (BASELINE.json `configs`):
+  N = 1 : C4 -- LP table over 2^28 build keys (8 GiB, far beyond L2), one step = one probe of
+          2^31 counter-generated keys (hit = 1) with dense (compacted) key+payload output.
+  N > 1 : C5 share per GPU (weak scaling) -- 2^27 build keys and 2^30 probe keys per rank,
+          both sides hash-partitioned and exchanged with an NCCL all-to-all; one step =
+          partition + exchange + local probe of every rank's probe keys.
+One JSON line on stdout (rank 0).  `--impl reference` times the reference's own CPU code
+(oracle/_ref/ref_driver, else the oracle port) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+PKG_NAME = "chunk-compaction-in-vectorized-execution-simd_b200"
+
+ALGO_BYTES_PER_TUPLE = 59.0  # 8 (key) + 32 * 1.1 (table sectors) + 16 * m (key + payload out), m = 1
+METRIC = "probe_tuples_per_sec"
+UNIT = "tuples/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def have_avx512() -> bool:
+    try:
+        flags = open("/proc/cpuinfo").read()
+        return all(x in flags for x in ("avx512f", "avx512dq", "avx512vl", "avx512bw"))
+    except OSError:
+        return False
+
+
+def cpu_sample(log2_build: int, log2_probe: int, procs: int, variants=(0,), include_single=True):
+    """Times the reference's CPU probe (LP, 2048-row chunks) on a bounded sample of the C4 workload:
+    same key generators, a 2^log2_build-key table (DRAM-resident on the host) and 2^log2_probe keys."""
+    import oracle_lib as O
+
+    n, nk = 1 << log2_build, 1 << log2_probe
+    keys = O.gen_keys_counter(nk, 2, n - 1)
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    out = {"sample": f"LP table 2^{log2_build} keys, 2^{log2_probe} probe keys (counter generator, hit=1), 2048-row chunks",
+           "cores": procs, "runs": {}}
+    if os.path.exists(drv) and have_avx512():
+        out["kind"] = "reference"
+        with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+            keys.tofile(f)
+            path = f.name
+        try:
+            names = {0: "scalar Probe+Next", 1: "AVX-512 SIMDProbe+SIMDNext", 2: "scalar InOneNext", 3: "AVX-512 SIMDInOneNext"}
+            for v in variants:
+                for p in (sorted({1, procs}) if include_single else [procs]):
+                    r = json.loads(subprocess.check_output([drv, "micro", "0", str(v), str(n), "1", "2048", path, str(nk), str(p)], timeout=900).decode().strip().splitlines()[-1])
+                    assert r["n_tuples"] == nk, r
+                    out["runs"][f"{names[v]} x{p}"] = nk / r["seconds"]
+        finally:
+            os.unlink(path)
+    else:
+        out["kind"] = "port"
+        out["cores"] = 1
+        tab = O.OracleLP(O.build_keys(n, 1))
+        t0 = time.perf_counter()
+        cnt, _ = O.microbench(tab, keys, 2048)
+        dt = time.perf_counter() - t0
+        assert cnt == nk
+        out["runs"]["oracle port scalar Probe+Next x1"] = nk / dt
+    out["value"] = max(out["runs"].values())
+    out["unit"] = UNIT
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = os.cpu_count() or 1
+    vals = []
+    t_start = time.perf_counter()
+    cb = None
+    for _ in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cb = cpu_sample(args.cpu_log2_build, args.cpu_log2_probe, procs, variants=(0, 1), include_single=False)
+        vals.append((cb["value"], time.perf_counter() - t0))
+        if time.perf_counter() - t_start > 240:
+            break
+    timed = vals[args.warmup:] or vals
+    value = statistics.mean(v for v, _ in timed)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "warmup": min(args.warmup, len(vals) - len(timed)),
+            "ms_per_step": 1e3 * statistics.mean(t for _, t in timed), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"], "runs": cb["runs"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args) -> dict:
+    if args.gpus == 1:
+        return {"workload": f"C4: LP hash join, 2^{args.log2_build} build keys (cf=1, {8 * 4 << args.log2_build >> 30} GiB table), "
+                            f"2^{args.log2_probe} probe keys/step (counter generator seed 2, hit=1), dense key+payload output",
+                "table": "linear_probing", "chunk": 1024, "l2_policy": "inputs (16 GiB keys, 8 GiB table) far exceed the 126 MB L2; no flush needed"}
+    return {"workload": f"C5 share: hash-partitioned LP join, per GPU 2^{args.log2_build} build keys and 2^{args.log2_probe} probe keys/step, "
+                        f"NCCL all-to-all exchange of both sides, dense key+payload output (results stay sharded)",
+            "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "l2_policy": "inputs far exceed L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-build", type=int, default=None, help="build keys per GPU (default 28 at N=1, 27 at N>1)")
+    ap.add_argument("--log2-probe", type=int, default=None, help="probe keys per GPU per step (default 31 at N=1, 30 at N>1)")
+    ap.add_argument("--e2e-log2-probe", type=int, default=28, help="probe keys of the host-buffer end-to-end sample")
+    ap.add_argument("--cpu-log2-build", type=int, default=24)
+    ap.add_argument("--cpu-log2-probe", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
+    if args.log2_build is None:
+        args.log2_build = 28 if args.gpus == 1 else 27
+    if args.log2_probe is None:
+        args.log2_probe = 31 if args.gpus == 1 else 30
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    pkg = importlib.import_module(PKG_NAME)
+    pkg.init(local_rank)
+    if distributed:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_build, n_probe = 1 << args.log2_build, 1 << args.log2_probe
+    peak, peak_src = measured_peak()
+    dev = torch.device("cuda", local_rank)
+
+    # ---- build side (untimed, like the reference: main.cpp:58-68 is outside the timer)
+    t0 = time.perf_counter()
+    if not distributed:
+        table = pkg.LPHashTable(n_build, 1)
+        join = None
+        key_space = n_build
+    else:
+        par = importlib.import_module(PKG_NAME + ".parallel")
+        key_space = n_build * world
+        local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
+        join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition")
+        table = join.table
+        del local_build
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    info = table.info()
+
+    # ---- probe side resident in HBM
+    keys = pkg.gen_keys_counter(n_probe, 2, key_space - 1, first=rank * n_probe)
+    cap = n_probe if not distributed else int(n_probe * 1.05) + (1 << 20)
+    out_key = torch.empty(cap, dtype=torch.int64, device=dev)
+    out_payload = torch.empty(cap, dtype=torch.int64, device=dev)
+    result = torch.zeros(4, dtype=torch.int64, device=dev)
+    recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if distributed else None
+    expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
+
+    def step():
+        if not distributed:
+            return table.probe_batch(keys, capacity=cap, out_key=out_key, out_payload=out_payload, result=result, sync=False)
+        shuffled = join.shuffle(keys, out=recv_buf)
+        return table.probe_batch(shuffled, capacity=cap, out_key=out_key, out_payload=out_payload, result=result, sync=False)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = pkg.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    t_all1.record()
+    barrier()
+    launches = pkg.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_all0.elapsed_time(t_all1)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    if distributed:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # ---- correctness properties at full size (hit = 1: every probe matches exactly once)
+    r = result.cpu().numpy().view(np.uint64)
+    n_matches, key_sum, payload_sum, overflow = int(r[0]), int(r[1]), int(r[2]), int(r[3])
+    if distributed:
+        n_matches, key_sum, payload_sum = par.reduce_result(n_matches, key_sum, payload_sum, dev)
+        t = torch.tensor([expected_sum - (1 << 64) if expected_sum >= (1 << 63) else expected_sum], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        expected_sum = int(t.item()) & ((1 << 64) - 1)
+    assert overflow == 0, "output capacity overflow"
+    assert n_matches == n_probe * world, (n_matches, n_probe * world)
+    assert key_sum == expected_sum and payload_sum == expected_sum, "checksum mismatch"
+
+    ms_per_step = total_ms / args.steps
+    value = n_probe * world / (ms_per_step * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": workload_config(args), "gpu_launches": int(launches), "clocks": clocks,
+            "build_seconds": build_s, "table": {"n_keys": int(info.n_keys), "n_slots": int(info.n_slots), "bytes": int(info.bytes)},
+            "checks": {"n_matches": n_matches, "key_sum_ok": True}}
+
+    if rank == 0 or not distributed:
+        # roofline of the dominant kernel (probe_batch_kernel): algorithmic bytes per launch / event time
+        if not distributed:
+            kernel_ms = statistics.mean(step_ms)
+            achieved = ALGO_BYTES_PER_TUPLE * n_probe / (kernel_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                "traffic": load_traffic(), "kernel": "probe_batch_kernel<LP,unique>", "kernel_ms": kernel_ms,
+                                "algorithmic_bytes_per_tuple": ALGO_BYTES_PER_TUPLE, "peak_source": peak_src}
+        else:
+            line["roofline"] = {"bound": "hbm", "achieved": ALGO_BYTES_PER_TUPLE * n_probe / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": ALGO_BYTES_PER_TUPLE * n_probe / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None,
+                                "note": "per-GPU, whole step (partition + all-to-all + probe); NVLink moves 8 B x (N-1)/N per key each way",
+                                "peak_source": peak_src}
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + probe + D2H inside the timed region)
+    if not args.no_e2e and not distributed:
+        del out_key, out_payload, keys
+        torch.cuda.empty_cache()
+        ne = 1 << min(args.e2e_log2_probe, args.log2_probe)
+        hk = torch.empty(ne, dtype=torch.int64).pin_memory()
+        hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345).cpu())
+        hok = torch.empty(ne, dtype=torch.int64).pin_memory()
+        hop = torch.empty(ne, dtype=torch.int64).pin_memory()
+        hk_np, hok_np, hop_np = hk.numpy(), hok.numpy(), hop.numpy()
+        table.probe_batch_host(hk_np, hok_np, hop_np)
+        ts = []
+        for _ in range(max(3, args.steps)):
+            t0 = time.perf_counter()
+            re = table.probe_batch_host(hk_np, hok_np, hop_np)
+            ts.append(time.perf_counter() - t0)
+        assert re["n_matches"] == ne and re["overflow"] == 0
+        assert np.array_equal(np.sort(hop_np[:1 << 16]), np.sort(hok_np[:1 << 16]))
+        e2e_s = statistics.mean(ts)
+        line["e2e"] = {"value": ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8, "d2h_bytes_per_step": ne * 16,
+                       "sample": f"2^{ne.bit_length() - 1} probe keys per call through cc_probe_batch_host (pinned host buffers, same table)",
+                       "ms_per_step": 1e3 * e2e_s}
+    elif distributed:
+        line["e2e"] = None
+
+    if rank == 0 and not args.no_cpu_baseline and not distributed:
+        try:
+            cb = cpu_sample(args.cpu_log2_build, args.cpu_log2_probe, os.cpu_count() or 1, variants=(0, 1))
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "runs")}
+        except Exception as e:  # the baseline is informative; never lose the GPU number over it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def load_traffic():
+    """dram bytes per launch of the probe kernel from the committed ncu capture (profiles/), if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "probe_batch_traffic.json")) as f:
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

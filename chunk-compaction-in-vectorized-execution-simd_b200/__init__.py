@@ -106,6 +106,15 @@ def gen_keys_counter(n: int, seed: int, mask: int, first: int = 0, out: Optional
     return out
 
 
+def set_probe_strategy(strategy: int = 0, slice_bytes: int = 0) -> None:
+    """0 auto, 1 direct, 2 partitioned (cc_probe_set_strategy)."""
+    L.check(lib().cc_probe_set_strategy(strategy, slice_bytes))
+
+
+def set_probe_cache_mode(mode_direct: int = 0, mode_partitioned: int = 2) -> None:
+    L.check(lib().cc_probe_set_cache_mode(mode_direct, mode_partitioned))
+
+
 # ---- data model (base.h:54-100) ---------------------------------------------------
 class Vector:
     """base.h:59-76: one column of kBlockSize int64 values (device resident, shared by reference)."""
@@ -337,7 +346,7 @@ class _TableBase:
         return b, c, k[: i.n_keys]
 
     def destroy(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().cc_ht_destroy(self._h)
             self._h = None
 

@@ -330,7 +330,7 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
   a.cap = a.materialize ? out_capacity : 0;
   for (size_t l = 0; l < n_joins; ++l) {
     const cc_ht *t = h_tables[l];
-    CC_REQUIRE(t && h_lhs_cols[l], "NULL table or column at level %zu", l);
+    CC_REQUIRE(t && (h_lhs_cols[l] || n_rows == 0), "NULL table or column at level %zu", l);
     CC_REQUIRE(t->n_slots <= (1ull << 32), "table at level %zu has more than 2^32 slots", l);
     ChainLevel &lv = a.lv[l];
     lv.slots = t->d_slots;

@@ -1,43 +1,80 @@
-// partition.cu -- hash partitioning for the multi-GPU partitioned join (SURVEY 8e;
-// new functionality, the reference is single-process).
+// partition.cu -- hash partitioning of a key column (new functionality).
 //
-// partition id = murmurhash64(key) >> (64 - log2 P): the HIGH hash bits, so the id is
-// independent of the low bits that pick the slot/bucket inside the owning GPU's table.
-// cc_partition_count builds the P-bin histogram with per-CTA shared-memory counters;
-// cc_partition_scatter groups the keys into P contiguous segments.  Each CTA ranks its
-// tile locally (shared-memory counters), reserves one contiguous range per partition
-// with a single global atomicAdd, and writes rows of the same partition at consecutive
-// addresses.  The exchange itself (all-to-all over NVLink) is issued by the host layer
-// (torch.distributed / NCCL) directly on the segment buffers.
+// One primitive, two users:
+//   * multi-GPU partitioned join: partition id = murmurhash64(key) >> (64 - log2 P), the HIGH
+//     hash bits, independent of the low bits that pick the slot/bucket inside the owner's table.
+//     The exchange itself (all-to-all over NVLink) is issued by the host layer (parallel.py).
+//   * single-GPU large tables (probe_batch.cu): partition id = the HIGH bits of the key's home
+//     slot / bucket index, so every partition probes one contiguous, L2-sized slice of the table
+//     ("radix pre-partition of probe keys into L2-sized slices").
+// Both are  id = ((hash & pre_mask) >> shift) & (P - 1).
+//
+// Two passes: a histogram (per-CTA shared-memory counters, one global atomic per bin per CTA),
+// then a scatter in which every CTA ranks its tile with shared-memory counters, reserves ONE
+// contiguous range per partition (global atomicAdd), sorts the tile by partition in shared
+// memory and writes it out so that consecutive threads store to consecutive addresses of the
+// same partition (coalesced runs instead of 8-byte scatters).
 #include "common.cuh"
+#include "partition.cuh"
 
 namespace ccb {
 
-constexpr int kPartThreads = 256;
-constexpr int kPartItems = 8;
-constexpr int kPartTile = kPartThreads * kPartItems;
-constexpr int kMaxParts = 256;
-
-__global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int64_t *__restrict__ keys, size_t n, int shift,
-                                                                       int parts, unsigned long long *counts) {
+__global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn,
+                                                                       unsigned long long *counts) {
   __shared__ uint32_t s_cnt[kMaxParts];
+  const int parts = (int) fn.pmask + 1;
   for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
   __syncthreads();
-  size_t stride = (size_t) gridDim.x * kPartThreads;
-  for (size_t i = (size_t) blockIdx.x * kPartThreads + threadIdx.x; i < n; i += stride) {
-    uint32_t p = shift >= 64 ? 0u : (uint32_t) (murmurhash64((uint64_t) keys[i]) >> shift);
-    atomicAdd(&s_cnt[p], 1u);
+  const size_t ntiles = (n + kPartTile - 1) / kPartTile;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t tbase = tile * (size_t) kPartTile;
+    uint64_t k[kPartItems];
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
+      k[j] = idx < n ? (uint64_t) __ldg(keys + idx) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
+      if (idx < n) atomicAdd(&s_cnt[fn(k[j])], 1u);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < parts; i += kPartThreads)
     if (s_cnt[i]) atomicAdd(counts + i, (unsigned long long) s_cnt[i]);
 }
 
+// exclusive scan of the P counters (single CTA), also resets the cursors
+__global__ void partition_offsets_kernel(const unsigned long long *__restrict__ counts, int parts, unsigned long long *offsets,
+                                         unsigned long long *cursors) {
+  __shared__ unsigned long long s[kMaxParts];
+  for (int i = threadIdx.x; i < parts; i += blockDim.x) s[i] = counts[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < parts; ++i) {
+      unsigned long long c = s[i];
+      s[i] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < parts; i += blockDim.x) {
+    offsets[i] = s[i];
+    cursors[i] = 0;
+  }
+}
+
 __global__ void __launch_bounds__(kPartThreads)
-    partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, int shift, int parts, const unsigned long long *__restrict__ offsets,
-                             unsigned long long *cursors, int64_t *out) {
+    partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
+                             unsigned long long *cursors, int64_t *__restrict__ out) {
+  __shared__ uint64_t s_sorted[kPartTile];
   __shared__ uint32_t s_cnt[kMaxParts];
-  __shared__ unsigned long long s_base[kMaxParts];
+  __shared__ uint32_t s_off[kMaxParts];
+  __shared__ unsigned long long s_gbase[kMaxParts];
+  __shared__ uint32_t s_warp[kPartThreads / 32];
+  const int parts = (int) fn.pmask + 1;
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
@@ -45,23 +82,76 @@ __global__ void __launch_bounds__(kPartThreads)
     uint64_t k[kPartItems];
     uint32_t p[kPartItems], r[kPartItems];
     const size_t tbase = tile * (size_t) kPartTile;
+    const uint32_t tile_n = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
+      k[j] = idx < n ? (uint64_t) __ldg(keys + idx) : 0;
+    }
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
       size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
       bool ok = idx < n;
-      k[j] = ok ? (uint64_t) __ldg(keys + idx) : 0;
-      p[j] = ok ? (shift >= 64 ? 0u : (uint32_t) (murmurhash64(k[j]) >> shift)) : 0xFFFFFFFFu;
+      p[j] = ok ? fn(k[j]) : 0xFFFFFFFFu;
       r[j] = ok ? atomicAdd(&s_cnt[p[j]], 1u) : 0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < parts; i += kPartThreads)
-      s_base[i] = s_cnt[i] ? offsets[i] + atomicAdd(cursors + i, (unsigned long long) s_cnt[i]) : 0ull;
+    // exclusive scan of the per-partition counts (parts <= kMaxParts = 4 * kPartThreads)
+    {
+      uint32_t c[kMaxParts / kPartThreads], tsum = 0;
+#pragma unroll
+      for (int q = 0; q < kMaxParts / kPartThreads; ++q) {
+        int i = threadIdx.x * (kMaxParts / kPartThreads) + q;
+        c[q] = i < parts ? s_cnt[i] : 0;
+        tsum += c[q];
+      }
+      uint32_t incl = warp_incl_scan_u32(tsum);
+      if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      uint32_t woff = 0;
+      for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) woff += s_warp[w];
+      uint32_t run = woff + incl - tsum;
+#pragma unroll
+      for (int q = 0; q < kMaxParts / kPartThreads; ++q) {
+        int i = threadIdx.x * (kMaxParts / kPartThreads) + q;
+        if (i < parts) {
+          s_off[i] = run;
+          s_gbase[i] = c[q] ? offsets[i] + atomicAdd(cursors + i, (unsigned long long) c[q]) : 0ull;
+        }
+        run += c[q];
+      }
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j)
-      if (p[j] != 0xFFFFFFFFu) out[s_base[p[j]] + r[j]] = (int64_t) k[j];
+      if (p[j] != 0xFFFFFFFFu) s_sorted[s_off[p[j]] + r[j]] = k[j];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
+      uint64_t key = s_sorted[i];
+      uint32_t pp = fn(key);
+      out[s_gbase[pp] + (i - s_off[pp])] = (int64_t) key;
+    }
     __syncthreads();
   }
+}
+
+int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st) {
+  const int parts = (int) fn.pmask + 1;
+  CC_CUDA(cudaMemsetAsync(d_counts, 0, parts * sizeof(unsigned long long), st));
+  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
+  if (blocks == 0) blocks = 1;
+  if (n) {
+    partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_counts);
+    CC_CHECK_LAUNCH();
+  }
+  partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors);
+  CC_CHECK_LAUNCH();
+  if (n) {
+    partition_scatter_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_offsets, d_cursors, d_out);
+    CC_CHECK_LAUNCH();
+  }
+  return CC_OK;
 }
 
 }  // namespace ccb
@@ -72,13 +162,13 @@ extern "C" {
 
 int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t *d_counts, cc_stream_t s) {
   CC_TRY(require_device());
-  CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxParts, "log2_parts must be in [0, 8]");
+  CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxParts, "log2_parts must be in [0, %d]", 9);
   CC_REQUIRE(d_counts && (n == 0 || d_keys), "NULL argument");
   int parts = 1 << log2_parts;
   CC_CUDA(cudaMemsetAsync(d_counts, 0, parts * sizeof(uint64_t), as_stream(s)));
   if (n == 0) return CC_OK;
-  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 8);
-  partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(d_keys, n, 64 - log2_parts, parts,
+  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
+  partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(d_keys, n, PartFn::high_bits(log2_parts),
                                                                               (unsigned long long *) d_counts);
   CC_CHECK_LAUNCH();
   return CC_OK;
@@ -87,14 +177,14 @@ int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t
 int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_offsets, uint64_t *d_cursors,
                          int64_t *d_out, cc_stream_t s) {
   CC_TRY(require_device());
-  CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxParts, "log2_parts must be in [0, 8]");
+  CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxParts, "log2_parts must be in [0, %d]", 9);
   CC_REQUIRE(d_offsets && d_cursors && (n == 0 || (d_keys && d_out)), "NULL argument");
   int parts = 1 << log2_parts;
   CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(uint64_t), as_stream(s)));
   if (n == 0) return CC_OK;
-  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 8);
+  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   partition_scatter_kernel<<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(
-      d_keys, n, 64 - log2_parts, parts, (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, d_out);
+      d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, d_out);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

@@ -1,0 +1,44 @@
+// partition.cuh -- shared by partition.cu and probe_batch.cu
+#pragma once
+#include "common.cuh"
+
+namespace ccb {
+
+constexpr int kPartThreads = 512;
+constexpr int kPartItems = 8;
+constexpr int kPartTile = kPartThreads * kPartItems;  // 4096 keys = 32 KiB of shared-memory staging
+constexpr int kMaxParts = 512;
+static_assert(kMaxParts % kPartThreads == 0, "scan assumes a whole number of bins per thread");
+
+// partition id = ((murmurhash64(key) & pre_mask) >> shift) & pmask
+struct PartFn {
+  uint64_t pre_mask;
+  uint32_t shift;
+  uint32_t pmask;
+  __host__ __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
+    uint64_t h = murmurhash64(key) & pre_mask;
+    return shift >= 64 ? 0u : ((uint32_t) (h >> shift) & pmask);
+  }
+  // multi-GPU owner: the high log2p bits of the hash
+  static PartFn high_bits(int log2p) {
+    PartFn f;
+    f.pre_mask = ~0ull;
+    f.shift = (uint32_t) (64 - log2p);
+    f.pmask = (1u << log2p) - 1u;
+    return f;
+  }
+  // table slice: the high log2p bits of the home slot / bucket index (table has 2^log2_slots entries)
+  static PartFn slot_bits(uint64_t table_mask, int log2_slots, int log2p) {
+    PartFn f;
+    f.pre_mask = table_mask;
+    f.shift = (uint32_t) (log2_slots - log2p);
+    f.pmask = (1u << log2p) - 1u;
+    return f;
+  }
+};
+
+// histogram + offsets + scatter on `st`; d_counts/d_offsets/d_cursors hold P entries each
+int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st);
+
+}  // namespace ccb

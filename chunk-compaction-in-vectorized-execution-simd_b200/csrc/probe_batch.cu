@@ -2,21 +2,39 @@
 // whole key column and writes dense (compacted) result columns.
 //
 // It is the fused GPU form of the micro-bench loop (simd_micro_bench.cpp:83-116:
-// Probe + while(HasNext) Next over every 2048-row chunk) followed by a Compactor on
-// every sparse result chunk (compactor.cpp:5-41):
-//   * a CTA iteration owns one chunk of kTile probe rows, kKeysPerThread per thread,
-//     loaded with coalesced strided loads so that all table accesses of a thread are
-//     independent and in flight together (memory-level parallelism for the gather);
-//   * a "round" is one Next(): every active lane compares its current slot / chain
-//     entry (ScanInnerJoin), matches are ranked with warp ballots + a 32-entry scan of
-//     the (key-slice, warp) counts, the CTA reserves a contiguous range of the global
-//     output with ONE atomicAdd, and the lanes store key and payload at consecutive
-//     positions (coalesced) -- the compaction step; then lanes advance
+// Probe + while(HasNext) Next over every chunk) followed by a Compactor on every sparse
+// result chunk (compactor.cpp:5-41):
+//   * a CTA iteration owns one chunk (tile) of kPbTile probe rows, kPbKeysPerThread per
+//     thread, loaded with coalesced strided loads so that all table accesses of a thread
+//     are independent and in flight together (memory-level parallelism for the gather);
+//     the NEXT tile's keys are requested into a second register set before this tile's
+//     gathers are consumed;
+//   * tiles are handed out by a global atomic counter, two iterations ahead.  This keeps
+//     all CTAs inside one narrow, moving window of the key column -- essential behind the
+//     partition pass: with static round-robin tiles the persistent CTAs drift apart by
+//     hundreds of tiles, the window spreads over many table slices and L2 thrashes
+//     (measured: 52 GB instead of 13 GB of DRAM reads for 2^29 keys, profiles/);
+//   * tables without duplicate keys: every thread walks its own probe sequences / chains
+//     to the first match (the walk past a match only ever finds duplicates,
+//     linear_probing_ht.cpp:101-109), then the CTA compacts once;
+//   * tables with duplicates: a "round" is one Next() -- every active lane compares its
+//     current slot / chain entry (ScanInnerJoin), matches are compacted, lanes advance
 //     (AdvancePointers) and finished lanes retire;
-//   * tables known to hold no duplicate key retire a lane at its first match (the
-//     walk past a match only ever finds duplicates, linear_probing_ht.cpp:101-109).
+//   * compaction step: matches are ranked with warp ballots + a 32-entry scan of the
+//     (key-slice, warp) counts, the CTA reserves a contiguous range of the global output
+//     with ONE atomicAdd, and lanes store key / payload at consecutive positions.
 // Output row order is unspecified; the multiset equals the reference's.
+//
+// Measured dead ends (B200, kept out of the code, evidence under profiles/):
+//   - streaming the keys through a TMA (cp.async.bulk + mbarrier) shared-memory ring: any
+//     sizeable shared-memory carve-out shrinks L1 and HALVES the gather rate of this chip
+//     (L2-resident 16 MiB gather: 290 G/s with <= 16 KiB smem per CTA, 138 G/s with 40 KiB);
+//   - L2::128B prefetch on the table loads: every miss then costs 4 sectors, no gain;
+//   - cudaLimitMaxL2FetchGranularity = 32: accepted, no effect on the 37 G/s big-table ceiling.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "partition.cuh"
 
 namespace ccb {
 
@@ -38,100 +56,214 @@ struct ProbeArgs {
   uint64_t *out_rowid;
   size_t cap;
   cc_probe_result *res;
+  unsigned long long *tile_counter;  // zero-initialised per launch
 };
 
-template <int KIND, bool UNIQUE>
-__global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a) {
-  __shared__ uint32_t s_cnt[32];
-  __shared__ unsigned long long s_base;
+// Cache mode HINT (MODE bit 1): L2 eviction priorities (createpolicy + L2::cache_hint) -- the
+// probe keys and the result columns are touched exactly once (evict_first, no L1 allocation),
+// the table is what must stay resident (evict_last).
+struct CachePolicy {
+  uint64_t first, last;
+};
+__device__ __forceinline__ CachePolicy make_policies() {
+  CachePolicy p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.last));
+  return p;
+}
+template <int MODE>
+__device__ __forceinline__ uint64_t ld_table_u64(const uint64_t *p, const CachePolicy &pol) {
+  uint64_t v;
+  if (MODE & 2)
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol.last));
+  else
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+template <int MODE>
+__device__ __forceinline__ uint2 ld_table_u32x2(const uint2 *p, const CachePolicy &pol) {
+  uint2 v;
+  if (MODE & 2)
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol.last));
+  else
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+template <int MODE>
+__device__ __forceinline__ uint64_t ld_stream_u64(const int64_t *p, const CachePolicy &pol) {
+  uint64_t v;
+  if (MODE & 2)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol.first));
+  else
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+template <int MODE>
+__device__ __forceinline__ void st_stream_u64(void *p, uint64_t v, const CachePolicy &pol) {
+  if (MODE & 2)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol.first) : "memory");
+  else
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct ProbeShared {
+  uint32_t cnt[32];
+  unsigned long long base;
+  unsigned long long tile_a, tile_b;  // tile indices handed out by the global counter
+};
+
+// Compaction step: rank the matches of the CTA, reserve a contiguous range of the global output
+// with ONE atomicAdd and store key / payload / row id at consecutive positions.
+template <int MODE>
+__device__ __forceinline__ void emit_matches(const ProbeArgs &a, ProbeShared &sh, const CachePolicy &pol, const bool (&m)[kPbKeysPerThread],
+                                             const uint64_t (&k)[kPbKeysPerThread], const uint64_t (&v)[kPbKeysPerThread],
+                                             size_t tbase, uint64_t &ksum, uint64_t &psum) {
   const unsigned w = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
+  unsigned bal[kPbKeysPerThread];
+#pragma unroll
+  for (int j = 0; j < kPbKeysPerThread; ++j) {
+    bal[j] = __ballot_sync(0xffffffffu, m[j]);
+    if (lane_id() == 0) sh.cnt[j * kPbWarps + w] = __popc(bal[j]);
+  }
+  __syncthreads();
+  if (w == 0) {
+    uint32_t c = sh.cnt[lane_id()];
+    uint32_t incl = warp_incl_scan_u32(c);
+    sh.cnt[lane_id()] = incl - c;
+    if (lane_id() == 31) sh.base = incl ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) incl) : 0ull;
+  }
+  __syncthreads();
+  const uint64_t base = sh.base;
+#pragma unroll
+  for (int j = 0; j < kPbKeysPerThread; ++j) {
+    if (m[j]) {
+      uint64_t dst = base + sh.cnt[j * kPbWarps + w] + __popc(bal[j] & lt);
+      ksum += k[j];
+      psum += v[j];
+      if (dst < a.cap) {
+        if (a.out_key) st_stream_u64<MODE>(a.out_key + dst, k[j], pol);
+        if (a.out_payload) st_stream_u64<MODE>(a.out_payload + dst, v[j], pol);
+        if (a.out_rowid) st_stream_u64<MODE>(a.out_rowid + dst, tbase + (size_t) j * kPbThreads + threadIdx.x, pol);
+      }
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, size_t tile, size_t ntiles,
+                                               uint64_t (&kn)[kPbKeysPerThread]) {
+  const size_t tbase = tile * (size_t) kPbTile;
+#pragma unroll
+  for (int j = 0; j < kPbKeysPerThread; ++j) {
+    size_t idx = tbase + (size_t) j * kPbThreads + threadIdx.x;
+    kn[j] = (tile < ntiles && idx < a.n) ? ld_stream_u64<MODE>(a.keys + idx, pol) : 0;
+  }
+}
+
+template <int KIND, bool UNIQUE, int MODE>
+__global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a) {
+  __shared__ ProbeShared sh;
+  const CachePolicy pol = make_policies();
   uint64_t ksum = 0, psum = 0;
   const size_t ntiles = (a.n + kPbTile - 1) / kPbTile;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // dynamic tile scheduling: `tile` is being processed, the keys of `ntile` are in flight, and
+  // thread 0 fetches the index after that while the CTA works (published through the emit barriers)
+  if (threadIdx.x == 0) {
+    sh.tile_a = atomicAdd(a.tile_counter, 1ull);
+    sh.tile_b = atomicAdd(a.tile_counter, 1ull);
+  }
+  __syncthreads();
+  size_t tile = (size_t) sh.tile_a, ntile = (size_t) sh.tile_b;
+  __syncthreads();
+  uint64_t kn[kPbKeysPerThread];
+  load_tile_keys<MODE>(a, pol, tile, ntiles, kn);
+  while (tile < ntiles) {
     const size_t tbase = tile * (size_t) kPbTile;
     uint64_t k[kPbKeysPerThread], v[kPbKeysPerThread], pos[kPbKeysPerThread];
     uint32_t end[kPbKeysPerThread];
     bool act[kPbKeysPerThread];
-    // ---- Probe (chaining_ht.cpp:44-55 / linear_probing_ht.cpp:45-57)
+    // ---- Probe (chaining_ht.cpp:44-55 / linear_probing_ht.cpp:45-57): all table loads of a thread in flight together
 #pragma unroll
     for (int j = 0; j < kPbKeysPerThread; ++j) {
-      size_t idx = tbase + (size_t) j * kPbThreads + threadIdx.x;
-      act[j] = idx < a.n;
-      k[j] = act[j] ? (uint64_t) __ldg(a.keys + idx) : 0;
+      act[j] = tbase + (size_t) j * kPbThreads + threadIdx.x < a.n;
+      k[j] = kn[j];
       pos[j] = murmurhash64(k[j]) & a.mask;
     }
     if (KIND == CC_HT_LP) {
 #pragma unroll
-      for (int j = 0; j < kPbKeysPerThread; ++j) v[j] = act[j] ? ld_nc_u64(a.slots + pos[j]) : kEmptyU;
+      for (int j = 0; j < kPbKeysPerThread; ++j) v[j] = act[j] ? ld_table_u64<MODE>(a.slots + pos[j], pol) : kEmptyU;
+      load_tile_keys<MODE>(a, pol, ntile, ntiles, kn);  // next tile's keys, behind this tile's gathers
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) act[j] = v[j] != kEmptyU;
     } else {
       uint2 d[kPbKeysPerThread];
 #pragma unroll
-      for (int j = 0; j < kPbKeysPerThread; ++j) d[j] = act[j] ? __ldg(a.dir + pos[j]) : make_uint2(0, 0);
+      for (int j = 0; j < kPbKeysPerThread; ++j) d[j] = act[j] ? ld_table_u32x2<MODE>(a.dir + pos[j], pol) : make_uint2(0, 0);
+      load_tile_keys<MODE>(a, pol, ntile, ntiles, kn);
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
         pos[j] = d[j].x;
         end[j] = d[j].x + d[j].y;
         act[j] = d[j].y != 0;
-        v[j] = act[j] ? (uint64_t) __ldg(a.ckeys + pos[j]) : 0;
+        v[j] = act[j] ? ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol) : 0;
       }
     }
-    // ---- rounds: one Next() each
-    bool any;
-    do {
+    if (threadIdx.x == 0) sh.tile_a = atomicAdd(a.tile_counter, 1ull);  // index for the iteration after next
+    if (UNIQUE) {
       bool m[kPbKeysPerThread];
-      unsigned bal[kPbKeysPerThread];
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
-        m[j] = act[j] && (v[j] == k[j]);
-        bal[j] = __ballot_sync(0xffffffffu, m[j]);
-        if (lane_id() == 0) s_cnt[j * kPbWarps + w] = __popc(bal[j]);
-      }
-      __syncthreads();
-      if (w == 0) {
-        uint32_t c = s_cnt[lane_id()];
-        uint32_t incl = warp_incl_scan_u32(c);
-        s_cnt[lane_id()] = incl - c;
-        if (lane_id() == 31) s_base = incl ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) incl) : 0ull;
-      }
-      __syncthreads();
-      const uint64_t base = s_base;
-#pragma unroll
-      for (int j = 0; j < kPbKeysPerThread; ++j) {
-        if (m[j]) {
-          uint64_t dst = base + s_cnt[j * kPbWarps + w] + __popc(bal[j] & lt);
-          ksum += k[j];
-          psum += v[j];
-          if (dst < a.cap) {
-            if (a.out_key) a.out_key[dst] = (int64_t) k[j];
-            if (a.out_payload) a.out_payload[dst] = (int64_t) v[j];
-            if (a.out_rowid) a.out_rowid[dst] = tbase + (size_t) j * kPbThreads + threadIdx.x;
+        bool hit = false;
+        while (act[j]) {
+          if (v[j] == k[j]) {
+            hit = true;
+            break;
           }
-        }
-      }
-      // ---- AdvancePointers (chaining_ht.cpp:109-124 / linear_probing_ht.cpp:100-110)
-      bool mine = false;
-#pragma unroll
-      for (int j = 0; j < kPbKeysPerThread; ++j) {
-        if (act[j]) {
-          if (UNIQUE && m[j]) {
-            act[j] = false;
-          } else if (KIND == CC_HT_LP) {
+          if (KIND == CC_HT_LP) {
             pos[j] = (pos[j] + 1) & a.mask;
-            v[j] = ld_nc_u64(a.slots + pos[j]);
+            v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
             act[j] = v[j] != kEmptyU;
           } else {
             pos[j] += 1;
             act[j] = pos[j] != end[j];
-            if (act[j]) v[j] = (uint64_t) __ldg(a.ckeys + pos[j]);
+            if (act[j]) v[j] = ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol);
           }
         }
-        mine |= act[j];
+        m[j] = hit;
       }
-      any = __syncthreads_or(mine);
-    } while (any);
+      emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
+    } else {
+      // ---- rounds: one Next() each (ScanInnerJoin + GatherResult + AdvancePointers)
+      bool any;
+      do {
+        bool m[kPbKeysPerThread];
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) m[j] = act[j] && (v[j] == k[j]);
+        emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
+        bool mine = false;
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) {
+          if (act[j]) {
+            if (KIND == CC_HT_LP) {
+              pos[j] = (pos[j] + 1) & a.mask;
+              v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
+              act[j] = v[j] != kEmptyU;
+            } else {
+              pos[j] += 1;
+              act[j] = pos[j] != end[j];
+              if (act[j]) v[j] = ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol);
+            }
+          }
+          mine |= act[j];
+        }
+        any = __syncthreads_or(mine);
+      } while (any);
+    }
+    // sh.tile_a was written before the barriers inside emit_matches: visible to everyone now
+    tile = ntile;
+    ntile = (size_t) sh.tile_a;
+    __syncthreads();  // protects sh.tile_a / sh.cnt / sh.base against the next iteration
   }
   ksum = warp_sum_u64(ksum);
   psum = warp_sum_u64(psum);
@@ -145,20 +277,57 @@ __global__ void probe_finish_kernel(cc_probe_result *res, size_t cap) {
   if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = res->n_matches > cap ? 1 : 0;
 }
 
-template <int KIND, bool UNIQUE>
+template <int KIND, bool UNIQUE, int MODE>
 static int launch_probe(const ProbeArgs &a, cudaStream_t st) {
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
-    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE>, kPbThreads, 0));
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE, MODE>, kPbThreads, 0));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
   size_t ntiles = (a.n + kPbTile - 1) / kPbTile;
   size_t grid = (size_t) sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid == 0) grid = 1;
-  probe_batch_kernel<KIND, UNIQUE><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
+  probe_batch_kernel<KIND, UNIQUE, MODE><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
   CC_CHECK_LAUNCH();
   return CC_OK;
+}
+
+template <int MODE>
+static int dispatch_probe_mode(const cc_ht *ht, const ProbeArgs &a, cudaStream_t st) {
+  bool unique = !ht->has_duplicates;
+  if (ht->kind == CC_HT_LP) return unique ? launch_probe<CC_HT_LP, true, MODE>(a, st) : launch_probe<CC_HT_LP, false, MODE>(a, st);
+  return unique ? launch_probe<CC_HT_CHAIN, true, MODE>(a, st) : launch_probe<CC_HT_CHAIN, false, MODE>(a, st);
+}
+
+static int dispatch_probe(int mode, const cc_ht *ht, const ProbeArgs &a, cudaStream_t st) {
+  return (mode & 2) ? dispatch_probe_mode<2>(ht, a, st) : dispatch_probe_mode<0>(ht, a, st);
+}
+
+// ---- strategy ------------------------------------------------------------------------------
+// direct      : probe the keys in input order (random gather over the whole table)
+// partitioned : first group the probe keys by table slice (partition.cu), then probe slice by
+//               slice so that the gather hits L2.  Pays one extra streaming pass over the keys
+//               (read 8 B + write 8 B per key, plus the 8 B histogram read) and wins whenever the
+//               table is far larger than L2: on B200 random 8-byte gathers over an 8 GiB table
+//               are capped at ~37 G/s by HBM (measured, profiles/), an L2-resident slice at ~290 G/s.
+static int g_strategy = 0;                // 0 auto, 1 direct, 2 partitioned
+static int g_mode_partitioned = 2;        // cache mode of the probe kernel behind the partition pass
+static int g_mode_direct = 0;             // cache mode of the direct probe
+static size_t g_slice_bytes = 16u << 20;  // target table bytes per partition (measured: 32 MiB slices already thrash L2)
+
+static int log2_floor(size_t x) {
+  int l = 0;
+  while ((x >> l) > 1) ++l;
+  return l;
+}
+
+static bool want_partitioned(const cc_ht *ht, size_t n, const uint64_t *d_out_rowid) {
+  if (d_out_rowid) return false;  // row ids refer to input order
+  if (g_strategy == 1) return false;
+  size_t table_bytes = ht->kind == CC_HT_LP ? ht->n_slots * 8 : ht->n_slots * 8 + ht->n_keys * 8;
+  if (g_strategy == 2) return table_bytes >= 2 * g_slice_bytes && n > 0;
+  return table_bytes >= ((size_t) 96 << 20) && n >= ((size_t) 1 << 22);
 }
 
 int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
@@ -175,13 +344,44 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
   a.out_rowid = d_out_rowid;
   a.cap = (d_out_key || d_out_payload || d_out_rowid) ? cap : 0;
   a.res = d_result;
+  a.tile_counter = nullptr;
   CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
   if (n) {
-    bool unique = !ht->has_duplicates;
-    if (ht->kind == CC_HT_LP)
-      CC_TRY(unique ? (launch_probe<CC_HT_LP, true>(a, st)) : (launch_probe<CC_HT_LP, false>(a, st)));
-    else
-      CC_TRY(unique ? (launch_probe<CC_HT_CHAIN, true>(a, st)) : (launch_probe<CC_HT_CHAIN, false>(a, st)));
+    const bool part = want_partitioned(ht, n, d_out_rowid);
+    size_t table_bytes = ht->kind == CC_HT_LP ? ht->n_slots * 8 : ht->n_slots * 8 + ht->n_keys * 8;
+    int log2_slots = log2_floor(ht->n_slots);
+    int log2p = log2_floor((table_bytes + g_slice_bytes - 1) / g_slice_bytes);
+    if ((size_t) 1 << log2p < (table_bytes + g_slice_bytes - 1) / g_slice_bytes) ++log2p;
+    if (log2p > log2_floor(kMaxParts)) log2p = log2_floor(kMaxParts);
+    if (log2p > log2_slots) log2p = log2_slots;
+    if (log2p < 1) log2p = 1;
+    const int parts = part ? 1 << log2p : 0;
+    // stream-ordered scratch: [tile counter | 3 x parts partition control words] (+ the partitioned keys)
+    unsigned long long *ctl = nullptr;
+    int64_t *scratch = nullptr;
+    CC_CUDA(cudaMallocAsync(&ctl, (8 + 3 * (size_t) parts) * sizeof(unsigned long long), st));
+    CC_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
+    a.tile_counter = ctl;
+    int rc = CC_OK;
+    if (part) {
+      cudaError_t e = cudaMallocAsync(&scratch, n * sizeof(int64_t), st);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeAsync(ctl, st);
+        set_error("partitioned probe: cannot allocate %zu bytes of scratch: %s", n * sizeof(int64_t), cudaGetErrorString(e));
+        return CC_ERR_NOMEM;
+      }
+      rc = partition_device(d_keys, n, PartFn::slot_bits(ht->mask, log2_slots, log2p), ctl + 8, ctl + 8 + parts, ctl + 8 + 2 * parts, scratch, st);
+      if (rc == CC_OK) {
+        a.keys = scratch;
+        rc = dispatch_probe(g_mode_partitioned, ht, a, st);
+      }
+      cudaFreeAsync(scratch, st);
+    } else {
+      rc = dispatch_probe(g_mode_direct, ht, a, st);
+    }
+    cudaFreeAsync(ctl, st);
+    CC_TRY(rc);
   }
   if (a.cap || d_out_key || d_out_payload || d_out_rowid) {
     probe_finish_kernel<<<1, 32, 0, st>>>(d_result, a.cap);
@@ -195,6 +395,20 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
 using namespace ccb;
 
 extern "C" {
+
+int cc_probe_set_strategy(int strategy, size_t slice_bytes) {
+  CC_REQUIRE(strategy >= 0 && strategy <= 2, "strategy must be 0 (auto), 1 (direct) or 2 (partitioned)");
+  g_strategy = strategy;
+  if (slice_bytes) g_slice_bytes = slice_bytes;
+  return CC_OK;
+}
+
+int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned) {
+  CC_REQUIRE((mode_direct & ~7) == 0 && (mode_partitioned & ~7) == 0, "cache modes are 0..7");
+  g_mode_direct = mode_direct;
+  g_mode_partitioned = mode_partitioned;
+  return CC_OK;
+}
 
 int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
                    uint64_t *d_out_rowid, size_t out_capacity, cc_probe_result *d_result, cc_stream_t s) {

@@ -107,6 +107,13 @@ int cc_device_init(int device) {
   CC_TRY(require_device());
   g_sm_count = 0;
   sm_count();
+  // keep stream-ordered scratch (cudaMallocAsync in the partitioned probe) cached between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
   return CC_OK;
 }
 

@@ -190,6 +190,17 @@ typedef struct {
 
 int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
                    uint64_t *d_out_rowid, size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
+/* Probe strategy for tables far larger than L2 (process-wide):
+ *   0 auto (default): partition the probe keys by table slice when the table is >= 96 MiB and
+ *     the batch >= 4 Mi keys and no row ids are requested; 1 always direct; 2 always partitioned.
+ * slice_bytes: target table bytes per partition (0 keeps the current value, default 16 MiB).
+ * The partitioned path needs n * 8 bytes of stream-ordered scratch (cudaMallocAsync).       */
+int cc_probe_set_strategy(int strategy, size_t slice_bytes);
+/* Cache behaviour of the probe kernel's memory operations (tuning knob; results never change):
+ *   bit 0: reserved (128-byte L2 line prefetch of table loads: measured harmful, ignored)
+ *   bit 1: L2 eviction priorities -- keys / result columns evict_first, table evict_last
+ * one mode for the direct probe (default 0), one for the probe behind the partition pass (default 2). */
+int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned);
 /* host-buffer convenience (the end-to-end path bench.py times as `e2e`): copies h_keys to
  * the device in slices, probes, copies the dense result columns back.          */
 int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_t *h_out_key, int64_t *h_out_payload,
@@ -271,7 +282,7 @@ int cc_tuner_destroy(cc_tuner *t);
  *   cc_partition_scatter: writes keys grouped by partition into d_out (P contiguous
  *                         segments at d_offsets[p]); optional row ids alongside.
  * The exchange itself (NCCL all-to-all over NVLink) is done by the host layer
- * on these buffers.                                                           */
+ * on these buffers.  log2_parts <= 9.                                          */
 int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t *d_counts, cc_stream_t stream);
 int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_offsets,
                          uint64_t *d_cursors, int64_t *d_out, cc_stream_t stream);

@@ -256,46 +256,66 @@ uint64_t MicroLoop(HT &table, const int64_t *keys, size_t nkeys, int variant) {
 
 template <class HT>
 int Micro(size_t n, size_t cf, const std::vector<int64_t> &keys, int variant, int procs) {
-  auto b0 = std::chrono::steady_clock::now();
-  HT table(n, cf);
-  double build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+  // procs > 1: fork FIRST, every worker builds its own private table (children of a process that
+  // already holds the table run ~3x slower per key here: copy-on-write heap traffic), then all
+  // workers start together on disjoint key ranges; throughput = all keys / slowest worker.
   uint64_t total = 0;
-  double secs = 0;
+  double secs = 0, build_s = 0;
   if (procs <= 1) {
+    auto b0 = std::chrono::steady_clock::now();
+    HT table(n, cf);
+    build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
     auto t0 = std::chrono::steady_clock::now();
     total = MicroLoop(table, keys.data(), keys.size(), variant);
     secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   } else {
-    std::vector<int> fds(procs);
+    std::vector<int> res_fd(procs), go_fd(procs), ready_fd(procs);
     std::vector<pid_t> pids(procs);
     size_t per = (keys.size() / procs / kBlockSize) * kBlockSize;
     if (per == 0) per = keys.size();
-    auto t0 = std::chrono::steady_clock::now();
     for (int p = 0; p < procs; ++p) {
-      int fd[2];
-      if (pipe(fd)) return 3;
+      int res[2], go[2], ready[2];
+      if (pipe(res) || pipe(go) || pipe(ready)) return 3;
       pid_t pid = fork();
       if (pid == 0) {
-        close(fd[0]);
+        close(res[0]);
+        close(go[1]);
+        close(ready[0]);
+        auto b0 = std::chrono::steady_clock::now();
+        HT table(n, cf);
+        double bs = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+        char c = 1;
+        if (write(ready[1], &c, 1) != 1 || read(go[0], &c, 1) != 1) _exit(4);
         size_t lo = std::min(keys.size(), (size_t) p * per);
         size_t hi = p == procs - 1 ? keys.size() : std::min(keys.size(), lo + per);
+        auto c0 = std::chrono::steady_clock::now();
         uint64_t r = MicroLoop(table, keys.data() + lo, hi - lo, variant);
-        if (write(fd[1], &r, 8) != 8) _exit(4);
+        double out[3] = {std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count(), (double) r, bs};
+        if (write(res[1], out, sizeof(out)) != (ssize_t) sizeof(out)) _exit(4);
         _exit(0);
       }
-      close(fd[1]);
-      fds[p] = fd[0];
+      close(res[1]);
+      close(go[0]);
+      close(ready[1]);
+      res_fd[p] = res[0];
+      go_fd[p] = go[1];
+      ready_fd[p] = ready[0];
       pids[p] = pid;
     }
+    char c = 0;
+    for (int p = 0; p < procs; ++p)
+      if (read(ready_fd[p], &c, 1) != 1) return 5;
+    for (int p = 0; p < procs; ++p)
+      if (write(go_fd[p], &c, 1) != 1) return 5;
     for (int p = 0; p < procs; ++p) {
-      uint64_t r = 0;
-      if (read(fds[p], &r, 8) != 8) return 5;
-      total += r;
-      close(fds[p]);
+      double out[3] = {0, 0, 0};
+      if (read(res_fd[p], out, sizeof(out)) != (ssize_t) sizeof(out)) return 5;
+      secs = std::max(secs, out[0]);
+      total += (uint64_t) out[1];
+      build_s = std::max(build_s, out[2]);
       int st;
       waitpid(pids[p], &st, 0);
     }
-    secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
   printf("{\"n_tuples\": %llu, \"seconds\": %.6f, \"build_seconds\": %.3f, \"probe_keys\": %zu, \"procs\": %d, \"variant\": %d}\n",
          (unsigned long long) total, secs, build_s, keys.size(), procs > 1 ? procs : 1, variant);

@@ -1,0 +1,92 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host layer: partition -> count exchange ->
+variable-size all-to-all -> local join.  The CUDA partition/probe kernels need a GPU, so the
+per-rank partitioning and local joins here use the ORACLE (test infrastructure) -- what is under
+test is parallel.py's exchange logic and the partition-id contract (high hash bits)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG_NAME, ROOT
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+
+    import oracle_lib as O
+
+    par = importlib.import_module(PKG_NAME + ".parallel")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        log2p = par.log2_exact(world)
+        n_build, n_probe = 5000, 40000
+        # range-partitioned inputs, as in bench.py: every rank owns a slice of the build keys (cf = 2)
+        build_all = O.build_keys(n_build * world, 2)
+        probe_all = O.gen_keys_counter(n_probe * world, 2, (1 << 14) - 1)
+        my_build = build_all[rank * n_build:(rank + 1) * n_build]
+        my_probe = probe_all[rank * n_probe:(rank + 1) * n_probe]
+
+        def shuffle(keys):
+            pid = (O.murmurhash64(keys.view(np.uint64)) >> np.uint64(64 - log2p)).astype(np.int64)
+            order = np.argsort(pid, kind="stable")
+            counts = np.bincount(pid, minlength=world)
+            send = torch.from_numpy(keys[order].copy())
+            recv_counts = par.exchange_counts(torch.from_numpy(counts.astype(np.int64)))
+            got = par.exchange_rows(send, counts.tolist(), recv_counts.tolist())
+            return got.numpy().copy()
+
+        mine_b = shuffle(my_build)
+        mine_p = shuffle(my_probe)
+        # ownership: every received key hashes to this rank
+        for arr in (mine_b, mine_p):
+            pid = O.murmurhash64(arr.view(np.uint64)) >> np.uint64(64 - log2p)
+            assert np.all(pid == rank)
+        local = O.pipeline([O.OracleLP(mine_b)], mine_p.reshape(-1, 1), 2048)
+        n, ks, ps = par.reduce_result(local["n_tuples"], local["colsum"][0], local["colsum"][2], torch.device("cpu"))
+        # single-process answer over the union
+        want = O.pipeline([O.OracleLP(build_all)], probe_all.reshape(-1, 1), 2048)
+        assert (n, ks, ps) == (want["n_tuples"], want["colsum"][0], want["colsum"][2])
+        # nothing lost or duplicated in the exchange
+        tot = torch.tensor([mine_b.size, mine_p.size], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert tot.tolist() == [n_build * world, n_probe * world]
+        assert par.choose_plan(2_000_000, 20_000_000 * 8, world) in ("broadcast", "partition")
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_join_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, "ok") for r in range(world)], results
+
+
+def test_plan_rule_and_log2():
+    import importlib
+
+    par = importlib.import_module(PKG_NAME + ".parallel")
+    assert par.log2_exact(8) == 3 and par.log2_exact(1) == 0
+    with pytest.raises(ValueError):
+        par.log2_exact(6)
+    # a 2M-key build against 8B probe keys is broadcast; 1B build against 8B probe is partitioned (C5)
+    assert par.choose_plan(2_000_000, 8 << 30, 8) == "broadcast"
+    assert par.choose_plan(1 << 30, 8 << 30, 8) == "partition"

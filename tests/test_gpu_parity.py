@@ -238,10 +238,22 @@ def test_facade_pipeline_matches_reference_tuples(ccb, name):
 
 
 # ------------------------------------------------------------------ batch probe (fast path)
+@pytest.fixture(params=["direct", "partitioned"])
+def strategy(request, ccb):
+    """Both probe strategies: direct, and key partitioning by table slice (forced, with tiny 16 KiB slices
+    so that even the small test tables are split into many partitions)."""
+    if request.param == "direct":
+        ccb.set_probe_strategy(1)
+    else:
+        ccb.set_probe_strategy(2, 16 << 10)
+    yield request.param
+    ccb.set_probe_strategy(0, 16 << 20)
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("n,cf,hit,nprobe", [(1024, 1, 1, 100000), (1024, 1, 2, 100000), (2000, 4, 1, 50000), (5000, 8, 4, 77777),
                                              (200000, 5, 1, 300000), (128, 1, 1, 1), (64, 2, 1, 0), (0, 1, 1, 1000)])
-def test_probe_batch_matches_oracle(ccb, kind, n, cf, hit, nprobe):
+def test_probe_batch_matches_oracle(ccb, strategy, kind, n, cf, hit, nprobe):
     rng = np.random.Generator(np.random.PCG64(n + cf + hit + nprobe))
     keys = rng.integers(0, max(1, n * hit), size=nprobe, dtype=np.int64)
     bk = O.build_keys(n, cf)
@@ -257,6 +269,10 @@ def test_probe_batch_matches_oracle(ccb, kind, n, cf, hit, nprobe):
     assert r["key_sum"] == u64sum(want["tuples"][:, 0]) and r["payload_sum"] == u64sum(want["tuples"][:, 2])
     rid = r["out_rowid"][:m].cpu().numpy()
     assert np.array_equal(keys[rid], got[:, 0])  # row ids point at the probe rows that produced the match
+    # without row ids the partitioned strategy is eligible: same multiset
+    r1 = gtab.probe_batch(dev(keys), capacity=cap)
+    got1 = np.stack([r1["out_key"][:m].cpu().numpy(), np.zeros(m, dtype=np.int64), r1["out_payload"][:m].cpu().numpy()], axis=1)
+    assert r1["n_matches"] == m and np.array_equal(G.sort_rows(got1), G.sort_rows(want["tuples"]))
     # count-only mode and the overflow report
     r2 = gtab.probe_batch(dev(keys), materialize=False)
     assert (r2["n_matches"], r2["key_sum"], r2["payload_sum"]) == (r["n_matches"], r["key_sum"], r["payload_sum"])
@@ -265,7 +281,7 @@ def test_probe_batch_matches_oracle(ccb, kind, n, cf, hit, nprobe):
         assert r3["overflow"] == 1 and r3["n_matches"] == m
 
 
-def test_probe_batch_negative_and_extreme_keys(ccb):
+def test_probe_batch_negative_and_extreme_keys(ccb, strategy):
     rng = np.random.Generator(np.random.PCG64(99))
     bk = rng.integers(-(1 << 62), 1 << 62, size=30000, dtype=np.int64)
     bk[bk == -1] = 5
@@ -289,10 +305,12 @@ def test_probe_batch_microbench_known_answer(ccb):
         assert r["n_matches"] == 67114250
 
 
-def test_probe_batch_large_properties(ccb):
+def test_probe_batch_large_properties(ccb, strategy):
     """Size-independent properties at a DRAM-resident size: hit=1 => every probe matches exactly once,
     key checksum == payload checksum == sum of inputs; hit=2 => matches are exactly the keys < n."""
     n = 1 << 24
+    if strategy == "partitioned":
+        ccb.set_probe_strategy(2, 8 << 20)
     for T in (ccb.LPHashTable, ccb.HashTable):
         tab = T(n, 1)
         assert tab.info().has_duplicates == 0
