@@ -70,9 +70,10 @@ __global__ void __launch_bounds__(kPartThreads)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
                              unsigned long long *cursors, int64_t *__restrict__ out) {
   __shared__ uint64_t s_sorted[kPartTile];
+  __shared__ uint16_t s_part[kPartTile];
   __shared__ uint32_t s_cnt[kMaxParts];
-  __shared__ uint32_t s_off[kMaxParts];
-  __shared__ unsigned long long s_gbase[kMaxParts];
+  __shared__ uint16_t s_off[kMaxParts];  // offsets inside the tile (< kPartTile)
+  __shared__ unsigned long long s_delta[kMaxParts];  // global base of the partition's run minus its offset in the tile
   __shared__ uint32_t s_warp[kPartThreads / 32];
   const int parts = (int) fn.pmask + 1;
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(kPartThreads)
       for (int q = 0; q < kMaxParts / kPartThreads; ++q) {
         int i = threadIdx.x * (kMaxParts / kPartThreads) + q;
         if (i < parts) {
-          s_off[i] = run;
-          s_gbase[i] = c[q] ? offsets[i] + atomicAdd(cursors + i, (unsigned long long) c[q]) : 0ull;
+          s_off[i] = (uint16_t) run;
+          s_delta[i] = c[q] ? offsets[i] + atomicAdd(cursors + i, (unsigned long long) c[q]) - run : 0ull;
         }
         run += c[q];
       }
@@ -124,13 +125,13 @@ __global__ void __launch_bounds__(kPartThreads)
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j)
-      if (p[j] != 0xFFFFFFFFu) s_sorted[s_off[p[j]] + r[j]] = k[j];
+      if (p[j] != 0xFFFFFFFFu) {
+        uint32_t slot = s_off[p[j]] + r[j];
+        s_sorted[slot] = k[j];
+        s_part[slot] = (uint16_t) p[j];
+      }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
-      uint64_t key = s_sorted[i];
-      uint32_t pp = fn(key);
-      out[s_gbase[pp] + (i - s_off[pp])] = (int64_t) key;
-    }
+    for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) out[s_delta[s_part[i]] + i] = (int64_t) s_sorted[i];
     __syncthreads();
   }
 }

@@ -42,6 +42,7 @@ constexpr int kPbThreads = 256;
 constexpr int kPbKeysPerThread = 4;
 constexpr int kPbWarps = kPbThreads / 32;
 constexpr int kPbTile = kPbThreads * kPbKeysPerThread;
+static_assert(kPbKeysPerThread == 4, "the interleaved walk tests act[0..3]");
 static_assert(kPbWarps * kPbKeysPerThread == 32, "rank scan assumes 32 (slice, warp) counters");
 
 struct ProbeArgs {
@@ -154,10 +155,16 @@ template <int MODE>
 __device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, size_t tile, size_t ntiles,
                                                uint64_t (&kn)[kPbKeysPerThread]) {
   const size_t tbase = tile * (size_t) kPbTile;
+  const int64_t *p = a.keys + tbase + threadIdx.x;
+  if (tbase + kPbTile <= a.n) {  // complete tile (CTA-uniform): no per-key bounds checks
 #pragma unroll
-  for (int j = 0; j < kPbKeysPerThread; ++j) {
-    size_t idx = tbase + (size_t) j * kPbThreads + threadIdx.x;
-    kn[j] = (tile < ntiles && idx < a.n) ? ld_stream_u64<MODE>(a.keys + idx, pol) : 0;
+    for (int j = 0; j < kPbKeysPerThread; ++j) kn[j] = ld_stream_u64<MODE>(p + j * kPbThreads, pol);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      size_t idx = tbase + (size_t) j * kPbThreads + threadIdx.x;
+      kn[j] = (tile < ntiles && idx < a.n) ? ld_stream_u64<MODE>(p + j * kPbThreads, pol) : 0;
+    }
   }
 }
 
@@ -184,9 +191,10 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
     uint32_t end[kPbKeysPerThread];
     bool act[kPbKeysPerThread];
     // ---- Probe (chaining_ht.cpp:44-55 / linear_probing_ht.cpp:45-57): all table loads of a thread in flight together
+    const bool full = tbase + kPbTile <= a.n;  // CTA-uniform
 #pragma unroll
     for (int j = 0; j < kPbKeysPerThread; ++j) {
-      act[j] = tbase + (size_t) j * kPbThreads + threadIdx.x < a.n;
+      act[j] = full || (tbase + (size_t) j * kPbThreads + threadIdx.x < a.n);
       k[j] = kn[j];
       pos[j] = murmurhash64(k[j]) & a.mask;
     }
@@ -211,26 +219,36 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
     }
     if (threadIdx.x == 0) sh.tile_a = atomicAdd(a.tile_counter, 1ull);  // index for the iteration after next
     if (UNIQUE) {
+      // walk all of the thread's probe sequences / chains together: one dependent load per lap for
+      // every key that has neither matched nor run out, instead of finishing key 0 before key 1
       bool m[kPbKeysPerThread];
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
-        bool hit = false;
-        while (act[j]) {
-          if (v[j] == k[j]) {
-            hit = true;
-            break;
-          }
-          if (KIND == CC_HT_LP) {
-            pos[j] = (pos[j] + 1) & a.mask;
-            v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
-            act[j] = v[j] != kEmptyU;
-          } else {
-            pos[j] += 1;
-            act[j] = pos[j] != end[j];
-            if (act[j]) v[j] = ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol);
+        m[j] = act[j] && (v[j] == k[j]);
+        act[j] = act[j] && !m[j];
+      }
+      while (act[0] | act[1] | act[2] | act[3]) {
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) {
+          if (act[j]) {
+            if (KIND == CC_HT_LP) {
+              pos[j] = (pos[j] + 1) & a.mask;
+              v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
+            } else {
+              pos[j] += 1;
+              act[j] = pos[j] != end[j];
+              if (act[j]) v[j] = ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol);
+            }
           }
         }
-        m[j] = hit;
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) {
+          if (act[j]) {
+            if (KIND == CC_HT_LP) act[j] = v[j] != kEmptyU;
+            m[j] = act[j] && (v[j] == k[j]);
+            act[j] = act[j] && !m[j];
+          }
+        }
       }
       emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
     } else {
