@@ -32,6 +32,7 @@
 //   - L2::128B prefetch on the table loads: every miss then costs 4 sectors, no gain;
 //   - cudaLimitMaxL2FetchGranularity = 32: accepted, no effect on the 37 G/s big-table ceiling.
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "partition.cuh"
@@ -345,7 +346,9 @@ static bool want_partitioned(const cc_ht *ht, size_t n, const uint64_t *d_out_ro
   if (g_strategy == 1) return false;
   size_t table_bytes = ht->kind == CC_HT_LP ? ht->n_slots * 8 : ht->n_slots * 8 + ht->n_keys * 8;
   if (g_strategy == 2) return table_bytes >= 2 * g_slice_bytes && n > 0;
-  return table_bytes >= ((size_t) 96 << 20) && n >= ((size_t) 1 << 22);
+  // auto: the table must be far beyond L2 AND the batch must revisit each 128-byte table line at
+  // least twice on average, otherwise grouping the keys buys no L2 reuse
+  return table_bytes >= ((size_t) 96 << 20) && n >= ((size_t) 1 << 22) && n >= table_bytes / 64;
 }
 
 int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
@@ -436,18 +439,14 @@ int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_
   return probe_batch_device(ht, d_keys, n, d_out_key, d_out_payload, d_out_rowid, out_capacity, d_result, as_stream(s));
 }
 
-// End-to-end convenience path with HOST buffers: slices of the key column are copied to the
-// device on one stream, probed on a second, and the dense result columns copied back on a
-// third, double-buffered so that PCIe traffic in both directions overlaps the kernel.
-int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_t *h_out_key, int64_t *h_out_payload,
-                        size_t out_capacity, cc_probe_result *h_result, cc_stream_t s) {
-  CC_TRY(require_device());
-  CC_REQUIRE(ht && h_result, "NULL argument");
-  CC_REQUIRE(n == 0 || h_keys, "h_keys is NULL");
-  (void) s;
-  constexpr int kBuf = 2;
-  const size_t slice = std::min<size_t>(n ? n : 1, (size_t) 1 << 25);  // 32 Mi keys = 256 MiB per slice
-  size_t out_slice_cap = slice * 2;
+// End-to-end path with HOST buffers: slices of the key column are copied to the device on one
+// stream, probed on a second, and the dense result columns copied back on a third, triple-buffered
+// so that PCIe traffic in both directions overlaps the kernels.  The device buffers, streams and
+// events live in a per-process workspace that is created on first use and reused by later calls
+// (allocation used to cost more than the transfers themselves).
+namespace {
+struct HostWs {
+  static constexpr int kBuf = 3;
   struct Buf {
     int64_t *d_keys = nullptr, *d_ok = nullptr, *d_op = nullptr;
     cc_probe_result *d_res = nullptr;
@@ -456,8 +455,10 @@ int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_
     size_t cap = 0;
   } buf[kBuf];
   cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-  int rc = CC_OK;
-  auto cleanup = [&]() {
+  size_t slice = 0;
+  int device = -1;
+  std::mutex mu;
+  void release() {
     for (auto &b : buf) {
       if (b.d_keys) cudaFree(b.d_keys);
       if (b.d_ok) cudaFree(b.d_ok);
@@ -467,77 +468,113 @@ int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_
       if (b.h2d_done) cudaEventDestroy(b.h2d_done);
       if (b.k_done) cudaEventDestroy(b.k_done);
       if (b.d2h_done) cudaEventDestroy(b.d2h_done);
+      b = Buf();
     }
     if (s_in) cudaStreamDestroy(s_in);
     if (s_k) cudaStreamDestroy(s_k);
     if (s_out) cudaStreamDestroy(s_out);
-  };
-#define CC_E2E(expr)                                                                    \
-  do {                                                                                  \
-    cudaError_t e__ = (expr);                                                           \
-    if (e__ != cudaSuccess) {                                                           \
-      set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
-      cleanup();                                                                        \
-      return e__ == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA;             \
-    }                                                                                   \
-  } while (0)
-  CC_E2E(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  CC_E2E(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-  CC_E2E(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-  const bool want_out = h_out_key || h_out_payload;
-  for (auto &b : buf) {
-    CC_E2E(cudaMalloc(&b.d_keys, slice * sizeof(int64_t)));
-    if (want_out) {
-      CC_E2E(cudaMalloc(&b.d_ok, out_slice_cap * sizeof(int64_t)));
-      CC_E2E(cudaMalloc(&b.d_op, out_slice_cap * sizeof(int64_t)));
-      b.cap = out_slice_cap;
-    }
-    CC_E2E(cudaMalloc(&b.d_res, sizeof(cc_probe_result)));
-    CC_E2E(cudaMallocHost(&b.h_res, sizeof(cc_probe_result)));
-    CC_E2E(cudaEventCreateWithFlags(&b.h2d_done, cudaEventDisableTiming));
-    CC_E2E(cudaEventCreateWithFlags(&b.k_done, cudaEventDisableTiming));
-    CC_E2E(cudaEventCreateWithFlags(&b.d2h_done, cudaEventDisableTiming));
+    s_in = s_k = s_out = nullptr;
+    slice = 0;
+    device = -1;
   }
-  cc_probe_result total = {0, 0, 0, 0};
-  size_t n_slices = (n + slice - 1) / slice;
-  auto issue = [&](size_t i) -> int {  // H2D + kernel for slice i
-    Buf &b = buf[i % kBuf];
-    size_t off = i * slice, cnt = std::min(slice, n - off);
-    // buffer reuse: the D2H of slice i-kBuf must have drained
-    if (i >= kBuf) {
-      cudaError_t e = cudaStreamWaitEvent(s_in, b.d2h_done, 0);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, b.d2h_done, 0);
-      if (e != cudaSuccess) return CC_ERR_CUDA;
+};
+HostWs g_ws;
+}  // namespace
+
+#define CC_E2E(expr)                                                                     \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      cudaGetLastError();                                                                \
+      return e__ == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA;              \
+    }                                                                                    \
+  } while (0)
+
+static int ws_prepare(HostWs &ws, size_t slice, bool want_out) {
+  int dev = 0;
+  CC_E2E(cudaGetDevice(&dev));
+  if (ws.device != dev || ws.slice < slice) {
+    ws.release();
+    ws.device = dev;
+    ws.slice = slice;
+    CC_E2E(cudaStreamCreateWithFlags(&ws.s_in, cudaStreamNonBlocking));
+    CC_E2E(cudaStreamCreateWithFlags(&ws.s_k, cudaStreamNonBlocking));
+    CC_E2E(cudaStreamCreateWithFlags(&ws.s_out, cudaStreamNonBlocking));
+    for (auto &b : ws.buf) {
+      CC_E2E(cudaMalloc(&b.d_keys, slice * sizeof(int64_t)));
+      CC_E2E(cudaMalloc(&b.d_res, sizeof(cc_probe_result)));
+      CC_E2E(cudaMallocHost(&b.h_res, sizeof(cc_probe_result)));
+      CC_E2E(cudaEventCreateWithFlags(&b.h2d_done, cudaEventDisableTiming));
+      CC_E2E(cudaEventCreateWithFlags(&b.k_done, cudaEventDisableTiming));
+      CC_E2E(cudaEventCreateWithFlags(&b.d2h_done, cudaEventDisableTiming));
     }
-    if (cudaMemcpyAsync(b.d_keys, h_keys + off, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, s_in) != cudaSuccess) return CC_ERR_CUDA;
-    if (cudaEventRecord(b.h2d_done, s_in) != cudaSuccess) return CC_ERR_CUDA;
-    if (cudaStreamWaitEvent(s_k, b.h2d_done, 0) != cudaSuccess) return CC_ERR_CUDA;
-    int r = probe_batch_device(ht, b.d_keys, cnt, b.d_ok, b.d_op, nullptr, b.cap, b.d_res, s_k);
-    if (r != CC_OK) return r;
-    if (cudaMemcpyAsync(b.h_res, b.d_res, sizeof(cc_probe_result), cudaMemcpyDeviceToHost, s_k) != cudaSuccess) return CC_ERR_CUDA;
-    if (cudaEventRecord(b.k_done, s_k) != cudaSuccess) return CC_ERR_CUDA;
+  }
+  if (want_out)
+    for (auto &b : ws.buf)
+      if (b.cap < slice) {
+        if (b.d_ok) cudaFree(b.d_ok);
+        if (b.d_op) cudaFree(b.d_op);
+        b.d_ok = b.d_op = nullptr;
+        b.cap = 0;
+        CC_E2E(cudaMalloc(&b.d_ok, slice * sizeof(int64_t)));
+        CC_E2E(cudaMalloc(&b.d_op, slice * sizeof(int64_t)));
+        b.cap = slice;
+      }
+  return CC_OK;
+}
+
+int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_t *h_out_key, int64_t *h_out_payload,
+                        size_t out_capacity, cc_probe_result *h_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(ht && h_result, "NULL argument");
+  CC_REQUIRE(n == 0 || h_keys, "h_keys is NULL");
+  (void) s;
+  HostWs &ws = g_ws;
+  std::lock_guard<std::mutex> lock(ws.mu);
+  constexpr int kBuf = HostWs::kBuf;
+  const size_t slice = std::min<size_t>(n ? n : 1, (size_t) 1 << 24);  // 16 Mi keys = 128 MiB per slice
+  const bool want_out = h_out_key || h_out_payload;
+  CC_TRY(ws_prepare(ws, slice, want_out));
+  cudaStream_t s_in = ws.s_in, s_k = ws.s_k, s_out = ws.s_out;
+  cc_probe_result total = {0, 0, 0, 0};
+  const size_t n_slices = (n + slice - 1) / slice;
+  auto issue = [&](size_t i) -> int {  // H2D + kernel for slice i
+    HostWs::Buf &b = ws.buf[i % kBuf];
+    size_t off = i * slice, cnt = std::min(slice, n - off);
+    if (i >= (size_t) kBuf) {  // buffer reuse: the D2H of slice i-kBuf must have drained
+      CC_E2E(cudaStreamWaitEvent(s_in, b.d2h_done, 0));
+      CC_E2E(cudaStreamWaitEvent(s_k, b.d2h_done, 0));
+    }
+    CC_E2E(cudaMemcpyAsync(b.d_keys, h_keys + off, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, s_in));
+    CC_E2E(cudaEventRecord(b.h2d_done, s_in));
+    CC_E2E(cudaStreamWaitEvent(s_k, b.h2d_done, 0));
+    CC_TRY(probe_batch_device(ht, b.d_keys, cnt, want_out ? b.d_ok : nullptr, want_out ? b.d_op : nullptr, nullptr, b.cap, b.d_res, s_k));
+    CC_E2E(cudaMemcpyAsync(b.h_res, b.d_res, sizeof(cc_probe_result), cudaMemcpyDeviceToHost, s_k));
+    CC_E2E(cudaEventRecord(b.k_done, s_k));
     return CC_OK;
   };
-  if (n_slices) rc = issue(0);
-  for (size_t i = 0; i < n_slices && rc == CC_OK; ++i) {
-    Buf &b = buf[i % kBuf];
-    if (i + 1 < n_slices) rc = issue(i + 1);
-    if (rc != CC_OK) break;
+  for (size_t i = 0; i < std::min<size_t>(n_slices, kBuf - 1); ++i) CC_TRY(issue(i));
+  for (size_t i = 0; i < n_slices; ++i) {
+    HostWs::Buf &b = ws.buf[i % kBuf];
+    if (i + kBuf - 1 < n_slices) CC_TRY(issue(i + kBuf - 1));
     CC_E2E(cudaEventSynchronize(b.k_done));
     cc_probe_result r = *b.h_res;
     if (want_out && r.n_matches > b.cap) {
       // fan-out above the slice buffer: grow this buffer and redo the slice (rare)
       CC_E2E(cudaStreamSynchronize(s_out));
+      CC_E2E(cudaStreamSynchronize(s_k));
       cudaFree(b.d_ok);
       cudaFree(b.d_op);
       b.d_ok = b.d_op = nullptr;
+      b.cap = 0;
+      CC_E2E(cudaMalloc(&b.d_ok, (size_t) r.n_matches * sizeof(int64_t)));
+      CC_E2E(cudaMalloc(&b.d_op, (size_t) r.n_matches * sizeof(int64_t)));
       b.cap = (size_t) r.n_matches;
-      CC_E2E(cudaMalloc(&b.d_ok, b.cap * sizeof(int64_t)));
-      CC_E2E(cudaMalloc(&b.d_op, b.cap * sizeof(int64_t)));
       size_t off = i * slice, cnt = std::min(slice, n - off);
-      rc = probe_batch_device(ht, b.d_keys, cnt, b.d_ok, b.d_op, nullptr, b.cap, b.d_res, s_k);
-      if (rc != CC_OK) break;
+      CC_TRY(probe_batch_device(ht, b.d_keys, cnt, b.d_ok, b.d_op, nullptr, b.cap, b.d_res, s_k));
       CC_E2E(cudaMemcpyAsync(b.h_res, b.d_res, sizeof(cc_probe_result), cudaMemcpyDeviceToHost, s_k));
+      CC_E2E(cudaEventRecord(b.k_done, s_k));
       CC_E2E(cudaStreamSynchronize(s_k));
       r = *b.h_res;
     }
@@ -556,15 +593,18 @@ int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_
     total.key_sum += r.key_sum;
     total.payload_sum += r.payload_sum;
   }
-  if (rc == CC_OK) {
-    CC_E2E(cudaStreamSynchronize(s_out));
-    CC_E2E(cudaStreamSynchronize(s_k));
-  }
-#undef CC_E2E
-  cleanup();
-  if (rc != CC_OK) return rc;
+  CC_E2E(cudaStreamSynchronize(s_out));
+  CC_E2E(cudaStreamSynchronize(s_k));
   *h_result = total;
   return CC_OK;
 }
+
+// frees the workspace of cc_probe_batch_host (device buffers, streams, events)
+int cc_probe_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_ws.mu);
+  g_ws.release();
+  return CC_OK;
+}
+#undef CC_E2E
 
 }  // extern "C"

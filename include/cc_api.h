@@ -191,8 +191,9 @@ typedef struct {
 int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
                    uint64_t *d_out_rowid, size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
 /* Probe strategy for tables far larger than L2 (process-wide):
- *   0 auto (default): partition the probe keys by table slice when the table is >= 96 MiB and
- *     the batch >= 4 Mi keys and no row ids are requested; 1 always direct; 2 always partitioned.
+ *   0 auto (default): partition the probe keys by table slice when the table is >= 96 MiB, the
+ *     batch holds >= max(4 Mi, table_bytes / 64) keys (each 128-byte table line is revisited)
+ *     and no row ids are requested; 1 always direct; 2 always partitioned.
  * slice_bytes: target table bytes per partition (0 keeps the current value, default 16 MiB).
  * The partitioned path needs n * 8 bytes of stream-ordered scratch (cudaMallocAsync).       */
 int cc_probe_set_strategy(int strategy, size_t slice_bytes);
@@ -205,6 +206,9 @@ int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned);
  * the device in slices, probes, copies the dense result columns back.          */
 int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_t *h_out_key, int64_t *h_out_payload,
                         size_t out_capacity, cc_probe_result *h_result, cc_stream_t stream);
+/* cc_probe_batch_host keeps its device staging buffers / streams in a per-process workspace
+ * (created on first use, reused afterwards); this releases it.                              */
+int cc_probe_host_release(void);
 
 /* -------------------------------------------------------------- compactor */
 /* NaiveCompactor (compactor.h:14-29, compactor.cpp:5-41), result-transparent
