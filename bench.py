@@ -174,8 +174,9 @@ def workload_config(args) -> dict:
                             f"2^{args.log2_probe} probe keys/step (counter generator seed 2, hit=1), dense key+payload output",
                 "table": "linear_probing", "chunk": 1024, "l2_policy": "inputs (16 GiB keys, 8 GiB table) far exceed the 126 MB L2; no flush needed"}
     return {"workload": f"C5 share: hash-partitioned LP join, per GPU 2^{args.log2_build} build keys and 2^{args.log2_probe} probe keys/step, "
-                        f"NCCL all-to-all exchange of both sides, dense key+payload output (results stay sharded)",
-            "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "l2_policy": "inputs far exceed L2; no flush needed"}
+                        f"exchange of both sides ({'scatter kernel stores into peer memory over NVLink' if args.exchange == 'p2p' else 'NCCL all-to-all'}), "
+                        f"dense key+payload output (results stay sharded)",
+            "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "exchange": args.exchange, "l2_policy": "inputs far exceed L2; no flush needed"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -192,6 +193,7 @@ def main() -> int:
     ap.add_argument("--cpu-log2-probe", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory scatter or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
@@ -232,7 +234,8 @@ def main() -> int:
         par = importlib.import_module(PKG_NAME + ".parallel")
         key_space = n_build * world
         local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
-        join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition")
+        join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
+                                   capacity_rows=int(n_probe * 1.05) + (1 << 20))
         table = join.table
         del local_build
     torch.cuda.synchronize()
@@ -245,7 +248,7 @@ def main() -> int:
     out_key = torch.empty(cap, dtype=torch.int64, device=dev)
     out_payload = torch.empty(cap, dtype=torch.int64, device=dev)
     result = torch.zeros(4, dtype=torch.int64, device=dev)
-    recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if distributed else None
+    recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if (distributed and args.exchange == "nccl") else None
     expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
 
     def step():

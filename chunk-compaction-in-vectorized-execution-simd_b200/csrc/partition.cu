@@ -14,6 +14,8 @@
 // contiguous range per partition (global atomicAdd), sorts the tile by partition in shared
 // memory and writes it out so that consecutive threads store to consecutive addresses of the
 // same partition (coalesced runs instead of 8-byte scatters).
+#include <cstring>
+
 #include "common.cuh"
 #include "partition.cuh"
 
@@ -66,9 +68,18 @@ __global__ void partition_offsets_kernel(const unsigned long long *__restrict__ 
   }
 }
 
+// PEERS == false: all partitions live in one local buffer `dst.p[0]`.
+// PEERS == true : partition p is written into dst.p[p] -- a buffer that may be PEER memory of another
+//                 GPU (CUDA IPC mapping over NVLink): the scatter IS the exchange, row runs travel as
+//                 coalesced stores straight into the owner's receive buffer.
+struct ScatterDst {
+  int64_t *p[kMaxPeers];
+};
+
+template <bool PEERS>
 __global__ void __launch_bounds__(kPartThreads)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
-                             unsigned long long *cursors, int64_t *__restrict__ out) {
+                             unsigned long long *cursors, ScatterDst dst) {
   __shared__ uint64_t s_sorted[kPartTile];
   __shared__ uint16_t s_part[kPartTile];
   __shared__ uint32_t s_cnt[kMaxParts];
@@ -131,7 +142,11 @@ __global__ void __launch_bounds__(kPartThreads)
         s_part[slot] = (uint16_t) p[j];
       }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) out[s_delta[s_part[i]] + i] = (int64_t) s_sorted[i];
+    for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
+      uint32_t pp = s_part[i];
+      int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
+      out[s_delta[pp] + i] = (int64_t) s_sorted[i];
+    }
     __syncthreads();
   }
 }
@@ -149,7 +164,9 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
   partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors);
   CC_CHECK_LAUNCH();
   if (n) {
-    partition_scatter_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_offsets, d_cursors, d_out);
+    ScatterDst dst;
+    dst.p[0] = d_out;
+    partition_scatter_kernel<false><<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst);
     CC_CHECK_LAUNCH();
   }
   return CC_OK;
@@ -184,9 +201,58 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
   CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(uint64_t), as_stream(s)));
   if (n == 0) return CC_OK;
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
-  partition_scatter_kernel<<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(
-      d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, d_out);
+  ScatterDst dst;
+  dst.p[0] = d_out;
+  partition_scatter_kernel<false><<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(
+      d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, dst);
   CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_base, uint64_t *d_cursors,
+                               int64_t *const *h_peer_bufs, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxPeers, "at most %d peers", kMaxPeers);
+  CC_REQUIRE(d_base && d_cursors && h_peer_bufs && (n == 0 || d_keys), "NULL argument");
+  int parts = 1 << log2_parts;
+  ScatterDst dst;
+  for (int p = 0; p < parts; ++p) {
+    CC_REQUIRE(h_peer_bufs[p], "NULL peer buffer %d", p);
+    dst.p[p] = h_peer_bufs[p];
+  }
+  CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(uint64_t), as_stream(s)));
+  if (n == 0) return CC_OK;
+  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
+  partition_scatter_kernel<true><<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(
+      d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_base, (unsigned long long *) d_cursors, dst);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// ---- CUDA IPC: map another rank's receive buffer into this process (one process per GPU) -------
+int cc_ipc_export(void *d_ptr, cc_ipc_handle *out) {
+  CC_TRY(require_device());
+  CC_REQUIRE(d_ptr && out, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(cc_ipc_handle), "handle size");
+  cudaIpcMemHandle_t h;
+  CC_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+  memset(out, 0, sizeof(*out));
+  memcpy(out->bytes, &h, sizeof(h));
+  return CC_OK;
+}
+
+int cc_ipc_open(const cc_ipc_handle *handle, void **d_ptr) {
+  CC_TRY(require_device());
+  CC_REQUIRE(handle && d_ptr, "NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle->bytes, sizeof(h));
+  CC_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return CC_OK;
+}
+
+int cc_ipc_close(void *d_ptr) {
+  if (!d_ptr) return CC_OK;
+  CC_CUDA(cudaIpcCloseMemHandle(d_ptr));
   return CC_OK;
 }
 

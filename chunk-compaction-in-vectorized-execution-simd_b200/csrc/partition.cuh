@@ -8,6 +8,7 @@ constexpr int kPartThreads = 512;
 constexpr int kPartItems = 8;
 constexpr int kPartTile = kPartThreads * kPartItems;  // 4096 keys = 32 KiB of shared-memory staging; measured: 2048-key tiles give 32-byte write runs and run 2x slower
 constexpr int kMaxParts = 512;
+constexpr int kMaxPeers = 16;  // destination buffers of the peer scatter (GPUs of one NVLink domain)
 static_assert(kMaxParts % kPartThreads == 0, "scan assumes a whole number of bins per thread");
 
 // partition id = ((murmurhash64(key) & pre_mask) >> shift) & pmask

@@ -56,16 +56,101 @@ def choose_plan(n_build_total: int, n_probe_total: int, world: int) -> str:
     return "broadcast" if n_build_total * 16 * world * 4 < n_probe_total * 8 else "partition"
 
 
+class PeerExchange:
+    """Fused scatter + exchange over peer memory (NVLink 5 / NVSwitch).
+
+    Every rank owns `n_buffers` receive buffers (plain cudaMalloc via cc_malloc) and maps the buffers
+    of all other ranks into its address space with CUDA IPC.  A shuffle is then
+        histogram -> all-gather of the P counts (tiny) -> ONE scatter kernel that stores every row
+        straight into its owner's receive buffer -> stream-ordered all-reduce as the barrier
+    i.e. the partition kernel IS the all-to-all: no staging copy, no second pass over the data, and
+    the NVLink transfer overlaps the kernel's own reads tile by tile.  Buffers alternate between
+    consecutive shuffles so that a fast rank can already scatter step i+1 while a slow one still
+    probes step i."""
+
+    def __init__(self, pkg, capacity_rows: int, group=None, n_buffers: int = 2):
+        import ctypes as C
+
+        self.pkg, self.group = pkg, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.log2p = log2_exact(self.world)
+        self.capacity = int(capacity_rows)
+        self.n_buffers = n_buffers
+        self.step = 0
+        lib = pkg.lib()
+        self.local, self.peers, self._opened = [], [], []
+        for _ in range(n_buffers):
+            ptr = C.c_void_p()
+            pkg._lib.check(lib.cc_malloc(C.byref(ptr), self.capacity * 8))
+            handle = (C.c_ubyte * 64)()
+            pkg._lib.check(lib.cc_ipc_export(ptr, handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(ptr.value)
+                else:
+                    hb = (C.c_ubyte * 64).from_buffer_copy(h)
+                    q = C.c_void_p()
+                    pkg._lib.check(lib.cc_ipc_open(hb, C.byref(q)))
+                    ptrs.append(q.value)
+                    self._opened.append(q.value)
+            self.local.append(ptr.value)
+            self.peers.append((C.c_void_p * self.world)(*ptrs))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        self._matrix = torch.zeros(self.world * self.world, dtype=torch.int64, device=dev)
+        self._cursors = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier(group=group)
+
+    def shuffle(self, keys: torch.Tensor) -> torch.Tensor:
+        """Hash-partition `keys` by owner and deliver them: returns this rank's rows (a view of the
+        current receive buffer, valid until the shuffle after next)."""
+        pkg, lib = self.pkg, self.pkg.lib()
+        stream = torch.cuda.current_stream().cuda_stream
+        n = keys.numel()
+        b = self.step % self.n_buffers
+        self.step += 1
+        pkg._lib.check(lib.cc_partition_count(keys.data_ptr() if n else None, n, self.log2p, self._counts.data_ptr(), stream))
+        dist.all_gather_into_tensor(self._matrix, self._counts, group=self.group)
+        m = self._matrix.view(self.world, self.world)  # m[sender][owner]
+        base = m[: self.rank].sum(dim=0).contiguous()  # rows of earlier senders in each owner's buffer
+        n_recv = int(m[:, self.rank].sum().item())
+        if n_recv > self.capacity:
+            raise RuntimeError(f"receive buffer too small: {n_recv} rows > capacity {self.capacity}")
+        pkg._lib.check(lib.cc_partition_scatter_peers(keys.data_ptr() if n else None, n, self.log2p, base.data_ptr(),
+                                                      self._cursors.data_ptr(), self.peers[b], stream))
+        dist.all_reduce(self._token, group=self.group)  # stream-ordered barrier: every rank's stores have landed
+        return pkg._wrap_ptr(self.local[b], max(n_recv, 1), torch.int64)[:n_recv]
+
+    def close(self) -> None:
+        lib = self.pkg.lib()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for q in self._opened:
+            lib.cc_ipc_close(q)
+        for p in self.local:
+            lib.cc_free(p)
+        self._opened, self.local = [], []
+
+
 class PartitionedJoin:
     """Build once, probe many times.  `pkg` is the product package (passed in to avoid a circular import)."""
 
-    def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition"):
+    def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition",
+                 exchange: str = "nccl", capacity_rows: int = 0):
+        """plan: "partition" (hash-partition both sides) or "broadcast" (replicate the build side).
+        exchange: "nccl" (scatter locally, then all_to_all_single) or "p2p" (PeerExchange: the scatter kernel
+        writes into the owners' buffers over NVLink); capacity_rows sizes the p2p receive buffers."""
         self.pkg = pkg
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.log2p = log2_exact(self.world)
         self.plan = plan
+        self.peer = PeerExchange(pkg, capacity_rows, group) if (exchange == "p2p" and plan == "partition") else None
         T = pkg.LPHashTable if kind == pkg.CC_HT_LP else pkg.HashTable
         if plan == "broadcast":
             n_local = torch.tensor([local_build_keys.numel()], dtype=torch.int64, device=local_build_keys.device)
@@ -88,6 +173,8 @@ class PartitionedJoin:
 
     def shuffle(self, keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Hash-partition `keys` and exchange: returns the rows this rank owns."""
+        if self.peer is not None:
+            return self.peer.shuffle(keys)
         part, counts, _ = self.pkg.partition_keys(keys, self.log2p)
         send_counts = torch.from_numpy(counts).to(keys.device)
         recv_counts = exchange_counts(send_counts, self.group)

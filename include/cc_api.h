@@ -290,6 +290,20 @@ int cc_tuner_destroy(cc_tuner *t);
 int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t *d_counts, cc_stream_t stream);
 int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_offsets,
                          uint64_t *d_cursors, int64_t *d_out, cc_stream_t stream);
+/* Fused scatter + exchange: partition p is written straight into h_peer_bufs[p], which may be the
+ * receive buffer of ANOTHER GPU mapped through CUDA IPC (stores travel over NVLink / NVSwitch).
+ * d_base[p] = first row of this rank's segment inside peer p's buffer (prefix over the senders of
+ * the all-gathered count matrix).  At most 16 peers.  The caller separates the scatter from the
+ * readers with a stream-ordered collective (e.g. an all-reduce), see parallel.py.               */
+int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_base,
+                               uint64_t *d_cursors, int64_t *const *h_peer_bufs, cc_stream_t stream);
+/* CUDA IPC plumbing for one-process-per-GPU peers (the pointer must come from cc_malloc). */
+typedef struct {
+  unsigned char bytes[64];
+} cc_ipc_handle;
+int cc_ipc_export(void *d_ptr, cc_ipc_handle *out);
+int cc_ipc_open(const cc_ipc_handle *handle, void **d_ptr);
+int cc_ipc_close(void *d_ptr);
 
 #ifdef __cplusplus
 }
