@@ -517,9 +517,31 @@ def chain_execute(tables: Sequence[_TableBase], lhs_cols: Sequence[torch.Tensor]
     return out
 
 
+def chain_execute_tuned(tables: Sequence[_TableBase], lhs_cols: Sequence[torch.Tensor], tuner: "CompactTuner", batch_rows: int,
+                        first_bandit_id: int = 0, materialize: bool = False, capacity: int = 0) -> dict:
+    """Dynamic compaction (main.cpp:137-167): thresholds chosen per batch by the tuner's bandits (cc_chain_execute_tuned)."""
+    _ensure()
+    J = len(tables)
+    n_rows = lhs_cols[0].numel()
+    tp = (C.c_void_p * J)(*[t._h for t in tables])
+    cp = (C.c_void_p * J)(*[c.data_ptr() for c in lhs_cols])
+    outs, op = None, None
+    if materialize:
+        outs = [torch.empty(max(capacity, 1), dtype=torch.int64, device="cuda") for _ in range(3 * J)]
+        op = (C.c_void_p * (3 * J))(*[o.data_ptr() for o in outs])
+    r = ChainResult()
+    L.check(lib().cc_chain_execute_tuned(tp, J, cp, n_rows, batch_rows, tuner._h, first_bandit_id, op, capacity, C.byref(r), _stream()))
+    out = _chain_result_dict(r, J)
+    out["out_cols"] = outs
+    return out
+
+
 def parse_chain_result(result: torch.Tensor, J: int) -> dict:
     raw = result.cpu().numpy().tobytes()
-    r = ChainResult.from_buffer_copy(raw)
+    return _chain_result_dict(ChainResult.from_buffer_copy(raw), J)
+
+
+def _chain_result_dict(r: ChainResult, J: int) -> dict:
     return dict(n_tuples=int(r.n_tuples), digest=int(r.digest), colsum=[int(r.colsum[i]) for i in range(3 * J)],
                 level_in=[int(r.level_in[i]) for i in range(J)], level_steps=[int(r.level_steps[i]) for i in range(J)],
                 level_lanes=[int(r.level_lanes[i]) for i in range(J)], overflow=int(r.overflow), device_ns=int(r.device_ns),

@@ -128,6 +128,7 @@ SIGNATURES = {
     "cc_compactor_flush": (_int, [_vp, _pvp, _pvp, C.POINTER(_sz), _vp]),
     "cc_compactor_destroy": (_int, [_vp]),
     "cc_chain_execute": (_int, [_pvp, _sz, _pvp, _sz, _vp, _pvp, _sz, _vp, _vp]),
+    "cc_chain_execute_tuned": (_int, [_pvp, _sz, _pvp, _sz, _sz, _vp, _sz, _pvp, _sz, C.POINTER(ChainResult), _vp]),
     "cc_tuner_create": (_int, [_pvp]),
     "cc_tuner_initialize": (_int, [_vp, _sz, _vp, _sz]),
     "cc_tuner_select_arm": (_int, [_vp, _sz, C.POINTER(_sz)]),

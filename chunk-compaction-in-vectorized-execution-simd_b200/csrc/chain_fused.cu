@@ -366,3 +366,77 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
+
+
+// Dynamic ("negative feedback") compaction: main.cpp:137-167 under flag_dynamic_compact.
+// The LHS table is processed in batches; before every batch each join's bandit picks a compaction
+// threshold (CompactTuner::SelectArm), the batch runs through the fused kernel, and every bandit is
+// rewarded with the reference's formula  2 / seconds / 1e3  (main.cpp:166) where seconds is the
+// DEVICE time of the batch (globaltimer, cc_chain_result.device_ns) -- a wall-clock reward would be
+// dominated by launch jitter.  Results are accumulated over the batches into *h_result.
+extern "C" int cc_chain_execute_tuned(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
+                                      size_t batch_rows, cc_tuner *tuner, size_t first_bandit_id, int64_t *const *h_out_cols,
+                                      size_t out_capacity, cc_chain_result *h_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(h_tables && h_lhs_cols && h_result && tuner, "NULL argument");
+  CC_REQUIRE(n_joins >= 1 && n_joins <= CC_MAX_JOINS, "n_joins must be in [1, %d]", CC_MAX_JOINS);
+  CC_REQUIRE(batch_rows > 0, "batch_rows must be > 0");
+  CC_REQUIRE(cc_tuner_bandit_size(tuner) >= first_bandit_id + n_joins, "tuner holds %zu bandits, need %zu", cc_tuner_bandit_size(tuner),
+             first_bandit_id + n_joins);
+  cudaStream_t st = as_stream(s);
+  cc_chain_result *d_res = nullptr, *h_pin = nullptr;
+  CC_CUDA(cudaMalloc(&d_res, sizeof(cc_chain_result)));
+  cudaError_t e = cudaMallocHost(&h_pin, sizeof(cc_chain_result));
+  if (e != cudaSuccess) {
+    cudaFree(d_res);
+    set_error("cudaMallocHost: %s", cudaGetErrorString(e));
+    return CC_ERR_NOMEM;
+  }
+  cc_chain_result total;
+  memset(&total, 0, sizeof(total));
+  int rc = CC_OK;
+  for (size_t start = 0; start < n_rows || (start == 0 && n_rows == 0); start += batch_rows) {
+    size_t cnt = n_rows - start < batch_rows ? n_rows - start : batch_rows;
+    const int64_t *cols[CC_MAX_JOINS];
+    int64_t *outs[3 * CC_MAX_JOINS];
+    uint32_t thr[CC_MAX_JOINS];
+    size_t arm[CC_MAX_JOINS];
+    for (size_t l = 0; l < n_joins; ++l) {
+      cols[l] = h_lhs_cols[l] ? h_lhs_cols[l] + start : nullptr;
+      rc = cc_tuner_select_arm(tuner, first_bandit_id + l, &arm[l]);  // main.cpp:140
+      if (rc != CC_OK) break;
+      thr[l] = (uint32_t) (arm[l] > 0xFFFFFFFFull ? 0xFFFFFFFFull : arm[l]);
+    }
+    if (rc != CC_OK) break;
+    size_t used = (size_t) total.n_tuples;
+    size_t room = h_out_cols && out_capacity > used ? out_capacity - used : 0;
+    if (h_out_cols)
+      for (size_t j = 0; j < 3 * n_joins; ++j) outs[j] = h_out_cols[j] + (used < out_capacity ? used : out_capacity);
+    rc = cc_chain_execute(h_tables, n_joins, cols, cnt, thr, (h_out_cols && room) ? outs : nullptr, room, d_res, s);
+    if (rc != CC_OK) break;
+    if (cudaMemcpyAsync(h_pin, d_res, sizeof(cc_chain_result), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("cc_chain_execute_tuned: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = CC_ERR_CUDA;
+      break;
+    }
+    double seconds = (double) h_pin->device_ns * 1e-9;
+    if (seconds > 0)
+      for (size_t l = 0; l < n_joins; ++l) cc_tuner_update_arm(tuner, first_bandit_id + l, arm[l], 2 / seconds / 1e3);  // main.cpp:166
+    total.n_tuples += h_pin->n_tuples;
+    total.digest += h_pin->digest;
+    for (size_t j = 0; j < 3 * n_joins; ++j) total.colsum[j] += h_pin->colsum[j];
+    for (size_t l = 0; l < n_joins; ++l) {
+      total.level_in[l] += h_pin->level_in[l];
+      total.level_steps[l] += h_pin->level_steps[l];
+      total.level_lanes[l] += h_pin->level_lanes[l];
+    }
+    total.device_ns += h_pin->device_ns;
+    if (h_out_cols && (h_pin->overflow || !room)) total.overflow = total.n_tuples > out_capacity ? 1 : 0;
+    if (n_rows == 0) break;
+  }
+  cudaFree(d_res);
+  cudaFreeHost(h_pin);
+  CC_TRY(rc);
+  *h_result = total;
+  return CC_OK;
+}

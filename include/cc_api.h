@@ -263,6 +263,15 @@ int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, const int64_t
                      const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
                      cc_chain_result *d_result, cc_stream_t stream);
 
+/* Dynamic ("negative feedback") compaction (main.cpp:137-167 under flag_dynamic_compact): the LHS table
+ * runs through cc_chain_execute in batches of batch_rows; before each batch bandit first_bandit_id + L
+ * of `tuner` selects the threshold of join L (SelectArm), afterwards every bandit is rewarded with
+ * 2 / seconds / 1e3 (main.cpp:166), seconds = device time of the batch.  Synchronous; the accumulated
+ * result is written to the HOST struct *h_result.                                                   */
+int cc_chain_execute_tuned(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
+                           size_t batch_rows, cc_tuner *tuner, size_t first_bandit_id, int64_t *const *h_out_cols,
+                           size_t out_capacity, cc_chain_result *h_result, cc_stream_t stream);
+
 /* ------------------------------------------------------ compaction policy */
 /* CompactTuner (negative_feedback.hpp:165-260) with one MultiArmedBandit
  * (:20-163) per join; FP64 arithmetic identical to the reference.            */

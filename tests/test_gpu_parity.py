@@ -470,3 +470,31 @@ def test_partition_kernels(ccb, log2p):
     for p in range(P):
         seg = out[offsets[p]:offsets[p] + counts[p]]
         assert np.array_equal(np.sort(seg), np.sort(keys[pid == p]))
+
+
+def test_chain_execute_tuned_negative_feedback(ccb):
+    """Dynamic compaction: bandit-chosen thresholds never change the result, and the policy learns that
+    compacting pays off on a sparse chain (most pulls go to the large thresholds)."""
+    J, cf, rhs, rows = 4, 8, 20000, 300000
+    lhs = O.gen_lhs_main(rows, J, rhs)
+    cols = [dev(lhs[:, j].copy()) for j in range(J)]
+    tables = [ccb.HashTable(rhs, cf) for _ in range(J)]
+    tuner = ccb.CompactTuner()
+    for l in range(J):
+        tuner.Initialize(0x1000 + l)
+    total_pulls = 0
+    for rep in range(12):  # 12 passes x 30 batches = 360 pulls per bandit (warm-up is 36)
+        r = ccb.chain_execute_tuned(tables, cols, tuner, batch_rows=10000)
+        assert (r["n_tuples"], r["digest"]) == (270336, 10954991527034855424)
+        assert r["level_in"][0] == rows
+        total_pulls += 30
+    arms = np.array(ccb.DEFAULT_ARMS)
+    for l in range(1, J):  # the compactors in front of joins 1..J-1 see sparse chunks
+        rewards, selects = ccb.CompactTuner.state(tuner, l - 1)
+        assert int(selects.sum()) == total_pulls
+        assert selects[arms >= 256].sum() > selects[arms < 64].sum(), (l, selects)
+    # materialised output across batches
+    r = ccb.chain_execute_tuned(tables, cols, tuner, batch_rows=77777, materialize=True, capacity=270336)
+    got = torch.stack([c[: r["n_tuples"]] for c in r["out_cols"]], dim=1).cpu().numpy()
+    want = O.pipeline([O.OracleChain(O.build_keys(rhs, cf)) for _ in range(J)], lhs, 256, collect=True)
+    assert r["overflow"] == 0 and np.array_equal(G.sort_rows(got), G.sort_rows(want["tuples"]))
