@@ -111,6 +111,17 @@ def set_probe_strategy(strategy: int = 0, slice_bytes: int = 0) -> None:
     L.check(lib().cc_probe_set_strategy(strategy, slice_bytes))
 
 
+def set_probe_profiling(enable: bool) -> None:
+    L.check(lib().cc_probe_set_profiling(int(enable)))
+
+
+def probe_last_phase_ms():
+    """(partition histogram, partition scatter, probe kernel) of the last cc_probe_batch, in ms."""
+    ms = (C.c_float * 3)()
+    L.check(lib().cc_probe_last_phase_ms(ms))
+    return [float(x) for x in ms]
+
+
 def set_probe_cache_mode(mode_direct: int = 0, mode_partitioned: int = 2) -> None:
     L.check(lib().cc_probe_set_cache_mode(mode_direct, mode_partitioned))
 

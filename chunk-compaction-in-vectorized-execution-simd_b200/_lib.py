@@ -119,6 +119,8 @@ SIGNATURES = {
     "cc_probe_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
     "cc_probe_set_strategy": (_int, [_int, _sz]),
     "cc_probe_set_cache_mode": (_int, [_int, _int]),
+    "cc_probe_set_profiling": (_int, [_int]),
+    "cc_probe_last_phase_ms": (_int, [_vp]),
     "cc_probe_batch_host": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(ProbeResult), _vp]),
     "cc_probe_host_release": (_int, []),
     "cc_compactor_create": (_int, [_pvp, _sz, _sz, _sz]),

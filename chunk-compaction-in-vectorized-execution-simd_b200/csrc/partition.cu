@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kPartThreads)
 }
 
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
-                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st) {
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count) {
   const int parts = (int) fn.pmask + 1;
   CC_CUDA(cudaMemsetAsync(d_counts, 0, parts * sizeof(unsigned long long), st));
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
@@ -163,6 +163,10 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
   }
   partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors);
   CC_CHECK_LAUNCH();
+  if (after_count) {
+    if (!*after_count) cudaEventCreate(after_count);
+    cudaEventRecord(*after_count, st);
+  }
   if (n) {
     ScatterDst dst;
     dst.p[0] = d_out;

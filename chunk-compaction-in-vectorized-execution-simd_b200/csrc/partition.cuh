@@ -39,7 +39,8 @@ struct PartFn {
 };
 
 // histogram + offsets + scatter on `st`; d_counts/d_offsets/d_cursors hold P entries each
+// after_count (optional): an event slot recorded between the histogram and the scatter (phase timing)
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
-                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st);
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count = nullptr);
 
 }  // namespace ccb

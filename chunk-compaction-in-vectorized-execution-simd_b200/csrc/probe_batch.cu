@@ -335,6 +335,16 @@ static int g_mode_partitioned = 2;        // cache mode of the probe kernel behi
 static int g_mode_direct = 0;             // cache mode of the direct probe
 static size_t g_slice_bytes = 16u << 20;  // target table bytes per partition (measured: 32 MiB slices already thrash L2)
 
+// optional live phase timing (bench.py): CUDA events on the launching stream around the three kernels
+static int g_profile = 0;
+static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static int g_ev_valid = 0;  // 0 nothing recorded, 1 direct (probe only), 2 partitioned (count, scatter, probe)
+static void profile_mark(int i, cudaStream_t st) {
+  if (!g_profile) return;
+  if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
+  cudaEventRecord(g_ev[i], st);
+}
+
 static int log2_floor(size_t x) {
   int l = 0;
   while ((x >> l) > 1) ++l;
@@ -392,14 +402,22 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
         set_error("partitioned probe: cannot allocate %zu bytes of scratch: %s", n * sizeof(int64_t), cudaGetErrorString(e));
         return CC_ERR_NOMEM;
       }
-      rc = partition_device(d_keys, n, PartFn::slot_bits(ht->mask, log2_slots, log2p), ctl + 8, ctl + 8 + parts, ctl + 8 + 2 * parts, scratch, st);
+      profile_mark(0, st);
+      rc = partition_device(d_keys, n, PartFn::slot_bits(ht->mask, log2_slots, log2p), ctl + 8, ctl + 8 + parts, ctl + 8 + 2 * parts, scratch, st,
+                            g_profile ? &g_ev[1] : nullptr);
+      profile_mark(2, st);
       if (rc == CC_OK) {
         a.keys = scratch;
         rc = dispatch_probe(g_mode_partitioned, ht, a, st);
       }
+      profile_mark(3, st);
+      g_ev_valid = g_profile ? 2 : 0;
       cudaFreeAsync(scratch, st);
     } else {
+      profile_mark(2, st);
       rc = dispatch_probe(g_mode_direct, ht, a, st);
+      profile_mark(3, st);
+      g_ev_valid = g_profile ? 1 : 0;
     }
     cudaFreeAsync(ctl, st);
     CC_TRY(rc);
@@ -421,6 +439,25 @@ int cc_probe_set_strategy(int strategy, size_t slice_bytes) {
   CC_REQUIRE(strategy >= 0 && strategy <= 2, "strategy must be 0 (auto), 1 (direct) or 2 (partitioned)");
   g_strategy = strategy;
   if (slice_bytes) g_slice_bytes = slice_bytes;
+  return CC_OK;
+}
+
+int cc_probe_set_profiling(int enable) {
+  g_profile = enable != 0;
+  g_ev_valid = 0;
+  return CC_OK;
+}
+
+int cc_probe_last_phase_ms(float *ms3) {
+  CC_REQUIRE(ms3, "NULL argument");
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  if (!g_ev_valid) return CC_OK;
+  CC_CUDA(cudaEventSynchronize(g_ev[3]));
+  if (g_ev_valid == 2) {
+    CC_CUDA(cudaEventElapsedTime(&ms3[0], g_ev[0], g_ev[1]));
+    CC_CUDA(cudaEventElapsedTime(&ms3[1], g_ev[1], g_ev[2]));
+  }
+  CC_CUDA(cudaEventElapsedTime(&ms3[2], g_ev[2], g_ev[3]));
   return CC_OK;
 }
 

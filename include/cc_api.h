@@ -202,6 +202,11 @@ int cc_probe_set_strategy(int strategy, size_t slice_bytes);
  *   bit 1: L2 eviction priorities -- keys / result columns evict_first, table evict_last
  * one mode for the direct probe (default 0), one for the probe behind the partition pass (default 2). */
 int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned);
+/* Live phase timing of cc_probe_batch (CUDA events on the launching stream): after enabling,
+ * cc_probe_last_phase_ms returns {partition histogram, partition scatter, probe kernel} of the
+ * most recent call in milliseconds (the first two are 0 for the direct strategy).            */
+int cc_probe_set_profiling(int enable);
+int cc_probe_last_phase_ms(float *ms3);
 /* host-buffer convenience (the end-to-end path bench.py times as `e2e`): copies h_keys to
  * the device in slices, probes, copies the dense result columns back.          */
 int cc_probe_batch_host(const cc_ht *ht, const int64_t *h_keys, size_t n, int64_t *h_out_key, int64_t *h_out_payload,
