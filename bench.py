@@ -190,9 +190,10 @@ def main() -> int:
     ap.add_argument("--log2-probe", type=int, default=None, help="probe keys per GPU per step (default 31 at N=1, 30 at N>1)")
     ap.add_argument("--e2e-log2-probe", type=int, default=28, help="probe keys of the host-buffer end-to-end sample")
     ap.add_argument("--cpu-log2-build", type=int, default=24)
-    ap.add_argument("--cpu-log2-probe", type=int, default=24)
+    ap.add_argument("--cpu-log2-probe", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sub-batches", type=int, default=1, help="N>1 with p2p: shuffle of sub-batch b+1 overlaps the probe of sub-batch b")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory scatter or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "ours":
@@ -245,17 +246,21 @@ def main() -> int:
     # ---- probe side resident in HBM
     keys = pkg.gen_keys_counter(n_probe, 2, key_space - 1, first=rank * n_probe)
     cap = n_probe if not distributed else int(n_probe * 1.05) + (1 << 20)
+    cap -= cap % max(1, args.sub_batches)
     out_key = torch.empty(cap, dtype=torch.int64, device=dev)
     out_payload = torch.empty(cap, dtype=torch.int64, device=dev)
-    result = torch.zeros(4, dtype=torch.int64, device=dev)
+    n_sub = args.sub_batches if (distributed and args.exchange == "p2p") else 1
+    result = torch.zeros((n_sub, 4), dtype=torch.int64, device=dev)
     recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if (distributed and args.exchange == "nccl") else None
     expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
 
     def step():
         if not distributed:
-            return table.probe_batch(keys, capacity=cap, out_key=out_key, out_payload=out_payload, result=result, sync=False)
+            return table.probe_batch(keys, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
+        if args.exchange == "p2p":
+            return join.probe_pipelined(keys, n_sub, out_key, out_payload, result)
         shuffled = join.shuffle(keys, out=recv_buf)
-        return table.probe_batch(shuffled, capacity=cap, out_key=out_key, out_payload=out_payload, result=result, sync=False)
+        return table.probe_batch(shuffled, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
 
     def barrier():
         if distributed:
@@ -295,7 +300,7 @@ def main() -> int:
         total_ms = float(t.item())
 
     # ---- correctness properties at full size (hit = 1: every probe matches exactly once)
-    r = result.cpu().numpy().view(np.uint64)
+    r = result.cpu().numpy().view(np.uint64).sum(axis=0, dtype=np.uint64)  # wrapping sums over the sub-batches
     n_matches, key_sum, payload_sum, overflow = int(r[0]), int(r[1]), int(r[2]), int(r[3])
     if distributed:
         n_matches, key_sum, payload_sum = par.reduce_result(n_matches, key_sum, payload_sum, dev)

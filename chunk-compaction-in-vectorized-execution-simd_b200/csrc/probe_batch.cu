@@ -152,21 +152,20 @@ __device__ __forceinline__ void emit_matches(const ProbeArgs &a, ProbeShared &sh
   }
 }
 
+// rows of tile `tile` that exist (0 .. kPbTile): the only 64-bit bounds arithmetic per tile, CTA-uniform
+__device__ __forceinline__ uint32_t tile_rows(size_t tile, size_t ntiles, size_t n) {
+  if (tile >= ntiles) return 0;
+  size_t rem = n - tile * (size_t) kPbTile;
+  return rem < (size_t) kPbTile ? (uint32_t) rem : (uint32_t) kPbTile;
+}
+
 template <int MODE>
-__device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, size_t tile, size_t ntiles,
+__device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, size_t tile, uint32_t rows,
                                                uint64_t (&kn)[kPbKeysPerThread]) {
-  const size_t tbase = tile * (size_t) kPbTile;
-  const int64_t *p = a.keys + tbase + threadIdx.x;
-  if (tbase + kPbTile <= a.n) {  // complete tile (CTA-uniform): no per-key bounds checks
+  const int64_t *p = a.keys + tile * (size_t) kPbTile + threadIdx.x;
 #pragma unroll
-    for (int j = 0; j < kPbKeysPerThread; ++j) kn[j] = ld_stream_u64<MODE>(p + j * kPbThreads, pol);
-  } else {
-#pragma unroll
-    for (int j = 0; j < kPbKeysPerThread; ++j) {
-      size_t idx = tbase + (size_t) j * kPbThreads + threadIdx.x;
-      kn[j] = (tile < ntiles && idx < a.n) ? ld_stream_u64<MODE>(p + j * kPbThreads, pol) : 0;
-    }
-  }
+  for (int j = 0; j < kPbKeysPerThread; ++j)
+    kn[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_stream_u64<MODE>(p + j * kPbThreads, pol) : 0;
 }
 
 template <int KIND, bool UNIQUE, int MODE>
@@ -185,31 +184,32 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
   size_t tile = (size_t) sh.tile_a, ntile = (size_t) sh.tile_b;
   __syncthreads();
   uint64_t kn[kPbKeysPerThread];
-  load_tile_keys<MODE>(a, pol, tile, ntiles, kn);
+  uint32_t rows = tile_rows(tile, ntiles, a.n);
+  load_tile_keys<MODE>(a, pol, tile, rows, kn);
   while (tile < ntiles) {
     const size_t tbase = tile * (size_t) kPbTile;
+    const uint32_t nrows = tile_rows(ntile, ntiles, a.n);
     uint64_t k[kPbKeysPerThread], v[kPbKeysPerThread], pos[kPbKeysPerThread];
     uint32_t end[kPbKeysPerThread];
     bool act[kPbKeysPerThread];
     // ---- Probe (chaining_ht.cpp:44-55 / linear_probing_ht.cpp:45-57): all table loads of a thread in flight together
-    const bool full = tbase + kPbTile <= a.n;  // CTA-uniform
 #pragma unroll
     for (int j = 0; j < kPbKeysPerThread; ++j) {
-      act[j] = full || (tbase + (size_t) j * kPbThreads + threadIdx.x < a.n);
+      act[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows;
       k[j] = kn[j];
       pos[j] = murmurhash64(k[j]) & a.mask;
     }
     if (KIND == CC_HT_LP) {
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) v[j] = act[j] ? ld_table_u64<MODE>(a.slots + pos[j], pol) : kEmptyU;
-      load_tile_keys<MODE>(a, pol, ntile, ntiles, kn);  // next tile's keys, behind this tile's gathers
+      load_tile_keys<MODE>(a, pol, ntile, nrows, kn);  // next tile's keys, behind this tile's gathers
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) act[j] = v[j] != kEmptyU;
     } else {
       uint2 d[kPbKeysPerThread];
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) d[j] = act[j] ? ld_table_u32x2<MODE>(a.dir + pos[j], pol) : make_uint2(0, 0);
-      load_tile_keys<MODE>(a, pol, ntile, ntiles, kn);
+      load_tile_keys<MODE>(a, pol, ntile, nrows, kn);
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
         pos[j] = d[j].x;
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
     }
     // sh.tile_a was written before the barriers inside emit_matches: visible to everyone now
     tile = ntile;
+    rows = nrows;
     ntile = (size_t) sh.tile_a;
     __syncthreads();  // protects sh.tile_a / sh.cnt / sh.base against the next iteration
   }

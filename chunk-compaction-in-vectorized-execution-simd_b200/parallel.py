@@ -68,7 +68,7 @@ class PeerExchange:
     consecutive shuffles so that a fast rank can already scatter step i+1 while a slow one still
     probes step i."""
 
-    def __init__(self, pkg, capacity_rows: int, group=None, n_buffers: int = 2):
+    def __init__(self, pkg, capacity_rows: int, group=None, n_buffers: int = 3):
         import ctypes as C
 
         self.pkg, self.group = pkg, group
@@ -105,9 +105,11 @@ class PeerExchange:
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.barrier(group=group)
 
-    def shuffle(self, keys: torch.Tensor) -> torch.Tensor:
-        """Hash-partition `keys` by owner and deliver them: returns this rank's rows (a view of the
-        current receive buffer, valid until the shuffle after next)."""
+    def shuffle(self, keys: torch.Tensor, reader_done: Optional[torch.cuda.Event] = None) -> torch.Tensor:
+        """Hash-partition `keys` by owner and deliver them: returns this rank's rows (a view of the current
+        receive buffer; it is overwritten by the n_buffers-th shuffle from now).
+        reader_done: event after which this rank no longer reads the buffer that the NEXT shuffle will
+        fill on the peers' behalf -- the barrier waits for it, so no peer can overwrite rows still in use."""
         pkg, lib = self.pkg, self.pkg.lib()
         stream = torch.cuda.current_stream().cuda_stream
         n = keys.numel()
@@ -122,6 +124,8 @@ class PeerExchange:
             raise RuntimeError(f"receive buffer too small: {n_recv} rows > capacity {self.capacity}")
         pkg._lib.check(lib.cc_partition_scatter_peers(keys.data_ptr() if n else None, n, self.log2p, base.data_ptr(),
                                                       self._cursors.data_ptr(), self.peers[b], stream))
+        if reader_done is not None:
+            torch.cuda.current_stream().wait_event(reader_done)
         dist.all_reduce(self._token, group=self.group)  # stream-ordered barrier: every rank's stores have landed
         return pkg._wrap_ptr(self.local[b], max(n_recv, 1), torch.int64)[:n_recv]
 
@@ -179,6 +183,34 @@ class PartitionedJoin:
         send_counts = torch.from_numpy(counts).to(keys.device)
         recv_counts = exchange_counts(send_counts, self.group)
         return exchange_rows(part, counts.tolist(), recv_counts.cpu().tolist(), out=out, group=self.group)
+
+    def probe_pipelined(self, local_probe_keys: torch.Tensor, n_sub: int, out_key: torch.Tensor, out_payload: torch.Tensor,
+                        results: torch.Tensor) -> None:
+        """One probe pass in n_sub sub-batches: the shuffle of sub-batch b+1 (NVLink-bound) runs on a side
+        stream while sub-batch b is probed on the current stream.  results: int64[n_sub, 4] device tensor
+        (one cc_probe_result per sub-batch); outputs are written into n_sub equal slices of out_key/out_payload.
+        Buffer safety: with 3 receive buffers a peer may only fill buffer k % 3 again at shuffle k + 3, i.e. after
+        it passed barrier k + 2, which this rank enters only once its probe of sub-batch k is complete."""
+        assert self.peer is not None, "pipelined probing needs the peer-memory exchange"
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_xstream"):
+            self._xstream = torch.cuda.Stream()
+            self._probe_done = {}
+        xs = self._xstream
+        xs.wait_stream(main)
+        cap = out_key.numel() // n_sub
+        for b, chunk in enumerate(local_probe_keys.chunk(n_sub)):
+            k = self.peer.step  # global shuffle index
+            with torch.cuda.stream(xs):
+                recv = self.peer.shuffle(chunk, reader_done=self._probe_done.pop(k - 2, None))
+                ready = torch.cuda.Event()
+                ready.record(xs)
+            main.wait_event(ready)
+            self.table.probe_batch(recv, capacity=cap, out_key=out_key[b * cap:(b + 1) * cap], out_payload=out_payload[b * cap:(b + 1) * cap],
+                                   result=results[b], sync=False)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._probe_done[k] = done
 
     def probe(self, local_probe_keys: torch.Tensor, **kw) -> dict:
         """One probe pass: (partition + all-to-all unless broadcast plan) + local batch probe."""
