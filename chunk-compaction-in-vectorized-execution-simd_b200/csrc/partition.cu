@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "partition.cuh"
+#include "tma.cuh"
 
 namespace ccb {
 
@@ -30,17 +31,14 @@ __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t tbase = tile * (size_t) kPartTile;
+    const uint32_t rows = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);  // CTA-uniform
+    const int64_t *src = keys + tbase + threadIdx.x;
     uint64_t k[kPartItems];
 #pragma unroll
-    for (int j = 0; j < kPartItems; ++j) {
-      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
-      k[j] = idx < n ? (uint64_t) __ldg(keys + idx) : 0;
-    }
+    for (int j = 0; j < kPartItems; ++j) k[j] = (uint32_t) (j * kPartThreads) + threadIdx.x < rows ? (uint64_t) __ldg(src + j * kPartThreads) : 0;
 #pragma unroll
-    for (int j = 0; j < kPartItems; ++j) {
-      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
-      if (idx < n) atomicAdd(&s_cnt[fn(k[j])], 1u);
-    }
+    for (int j = 0; j < kPartItems; ++j)
+      if ((uint32_t) (j * kPartThreads) + threadIdx.x < rows) atomicAdd(&s_cnt[fn(k[j])], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < parts; i += kPartThreads)
@@ -76,44 +74,77 @@ struct ScatterDst {
   int64_t *p[kMaxPeers];
 };
 
-template <bool PEERS>
+// TMA == true: the NEXT tile of keys is pulled into shared memory by one cp.async.bulk (UBLKCP) while the
+// CTA ranks / sorts / stores the current one, so the key stream never waits behind the tile's barriers.
+// (Unlike the probe kernel this kernel does no gathers, so the larger shared-memory carve-out costs nothing.)
+template <bool PEERS, bool TMA>
 __global__ void __launch_bounds__(kPartThreads)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
                              unsigned long long *cursors, ScatterDst dst) {
-  __shared__ uint64_t s_sorted[kPartTile];
-  __shared__ uint16_t s_part[kPartTile];
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  uint64_t *s_sorted = reinterpret_cast<uint64_t *>(s_dyn);                  // [kPartTile]
+  uint64_t *s_in = s_sorted + kPartTile;                                       // [kPartTile] (TMA only)
+  uint16_t *s_part = reinterpret_cast<uint16_t *>(s_dyn + (TMA ? 2 : 1) * kPartTile * sizeof(uint64_t));  // [kPartTile]
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_cnt[kMaxParts];
   __shared__ uint16_t s_off[kMaxParts];  // offsets inside the tile (< kPartTile)
   __shared__ unsigned long long s_delta[kMaxParts];  // global base of the partition's run minus its offset in the tile
   __shared__ uint32_t s_warp[kPartThreads / 32];
   const int parts = (int) fn.pmask + 1;
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
+  const size_t nfull = n / kPartTile;  // complete tiles travel through the TMA buffer, the ragged tail is loaded directly
+  uint32_t phase = 0;
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (size_t) blockIdx.x < nfull) {
+      mbar_expect_tx(&s_bar, kPartTile * 8);
+      tma_load_1d(s_in, keys + (size_t) blockIdx.x * kPartTile, kPartTile * 8, &s_bar);
+    }
+  }
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
-    __syncthreads();
     uint64_t k[kPartItems];
     uint32_t p[kPartItems], r[kPartItems];
     const size_t tbase = tile * (size_t) kPartTile;
-    const uint32_t tile_n = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);
+    const uint32_t tile_n = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);  // CTA-uniform
+    if (TMA && tile < nfull) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
 #pragma unroll
-    for (int j = 0; j < kPartItems; ++j) {
-      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
-      k[j] = idx < n ? (uint64_t) __ldg(keys + idx) : 0;
+      for (int j = 0; j < kPartItems; ++j) k[j] = s_in[j * kPartThreads + threadIdx.x];
+      __syncthreads();  // every thread holds its keys (and s_cnt is cleared): the buffer may be refilled
+      if (threadIdx.x == 0 && tile + gridDim.x < nfull) {
+        mbar_expect_tx(&s_bar, kPartTile * 8);
+        tma_load_1d(s_in, keys + (tile + gridDim.x) * (size_t) kPartTile, kPartTile * 8, &s_bar);
+      }
+    } else {
+      __syncthreads();
+      const int64_t *src = keys + tbase + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < kPartItems; ++j) k[j] = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n ? (uint64_t) __ldg(src + j * kPartThreads) : 0;
     }
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
-      size_t idx = tbase + (size_t) j * kPartThreads + threadIdx.x;
-      bool ok = idx < n;
+      bool ok = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n;
       p[j] = ok ? fn(k[j]) : 0xFFFFFFFFu;
       r[j] = ok ? atomicAdd(&s_cnt[p[j]], 1u) : 0;
     }
     __syncthreads();
-    // exclusive scan of the per-partition counts (parts <= kMaxParts = 4 * kPartThreads)
+    // exclusive scan of the per-partition counts (parts <= kMaxParts = kBins * kPartThreads).  The global
+    // range reservations (one atomicAdd per non-empty partition) are ISSUED here but only consumed after the
+    // shared-memory sort below, so their L2 round trip overlaps that phase instead of stalling the CTA.
+    constexpr int kBins = kMaxParts / kPartThreads;
+    unsigned long long gbase[kBins];
+    uint32_t first[kBins];
     {
-      uint32_t c[kMaxParts / kPartThreads], tsum = 0;
+      uint32_t c[kBins], tsum = 0;
 #pragma unroll
-      for (int q = 0; q < kMaxParts / kPartThreads; ++q) {
-        int i = threadIdx.x * (kMaxParts / kPartThreads) + q;
+      for (int q = 0; q < kBins; ++q) {
+        int i = threadIdx.x * kBins + q;
         c[q] = i < parts ? s_cnt[i] : 0;
         tsum += c[q];
       }
@@ -124,11 +155,13 @@ __global__ void __launch_bounds__(kPartThreads)
       for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) woff += s_warp[w];
       uint32_t run = woff + incl - tsum;
 #pragma unroll
-      for (int q = 0; q < kMaxParts / kPartThreads; ++q) {
-        int i = threadIdx.x * (kMaxParts / kPartThreads) + q;
+      for (int q = 0; q < kBins; ++q) {
+        int i = threadIdx.x * kBins + q;
+        first[q] = run;
+        gbase[q] = 0;
         if (i < parts) {
           s_off[i] = (uint16_t) run;
-          s_delta[i] = c[q] ? offsets[i] + atomicAdd(cursors + i, (unsigned long long) c[q]) - run : 0ull;
+          if (c[q]) gbase[q] = offsets[i] + atomicAdd(cursors + i, (unsigned long long) c[q]);
         }
         run += c[q];
       }
@@ -141,6 +174,11 @@ __global__ void __launch_bounds__(kPartThreads)
         s_sorted[slot] = k[j];
         s_part[slot] = (uint16_t) p[j];
       }
+#pragma unroll
+    for (int q = 0; q < kBins; ++q) {
+      int i = threadIdx.x * kBins + q;
+      if (i < parts) s_delta[i] = gbase[q] - first[q];
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
       uint32_t pp = s_part[i];
@@ -149,6 +187,22 @@ __global__ void __launch_bounds__(kPartThreads)
     }
     __syncthreads();
   }
+}
+
+template <bool PEERS>
+static int launch_scatter(const int64_t *d_keys, size_t n, PartFn fn, const unsigned long long *d_offsets, unsigned long long *d_cursors,
+                          const ScatterDst &dst, size_t blocks, cudaStream_t st) {
+  const bool tma = (reinterpret_cast<uintptr_t>(d_keys) & 15) == 0;  // bulk copies need 16-byte alignment
+  const size_t smem = (tma ? 2 : 1) * (size_t) kPartTile * sizeof(uint64_t) + (size_t) kPartTile * sizeof(uint16_t);
+  if (tma) {
+    CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst);
+  } else {
+    CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    partition_scatter_kernel<PEERS, false><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst);
+  }
+  CC_CHECK_LAUNCH();
+  return CC_OK;
 }
 
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
@@ -170,8 +224,7 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
   if (n) {
     ScatterDst dst;
     dst.p[0] = d_out;
-    partition_scatter_kernel<false><<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst);
-    CC_CHECK_LAUNCH();
+    CC_TRY(launch_scatter<false>(d_keys, n, fn, d_offsets, d_cursors, dst, blocks, st));
   }
   return CC_OK;
 }
@@ -207,10 +260,8 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   ScatterDst dst;
   dst.p[0] = d_out;
-  partition_scatter_kernel<false><<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(
-      d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, dst);
-  CC_CHECK_LAUNCH();
-  return CC_OK;
+  return launch_scatter<false>(d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, dst,
+                               blocks, as_stream(s));
 }
 
 int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_base, uint64_t *d_cursors,
@@ -227,10 +278,8 @@ int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, 
   CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(uint64_t), as_stream(s)));
   if (n == 0) return CC_OK;
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
-  partition_scatter_kernel<true><<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(
-      d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_base, (unsigned long long *) d_cursors, dst);
-  CC_CHECK_LAUNCH();
-  return CC_OK;
+  return launch_scatter<true>(d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_base, (unsigned long long *) d_cursors, dst,
+                              blocks, as_stream(s));
 }
 
 // ---- CUDA IPC: map another rank's receive buffer into this process (one process per GPU) -------

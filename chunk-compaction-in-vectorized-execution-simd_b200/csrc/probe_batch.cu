@@ -137,13 +137,14 @@ __device__ __forceinline__ void emit_matches(const ProbeArgs &a, ProbeShared &sh
   }
   __syncthreads();
   const uint64_t base = sh.base;
+  const bool fits = base + kPbTile <= a.cap;  // CTA-uniform: the whole tile fits, no per-row capacity check
 #pragma unroll
   for (int j = 0; j < kPbKeysPerThread; ++j) {
     if (m[j]) {
       uint64_t dst = base + sh.cnt[j * kPbWarps + w] + __popc(bal[j] & lt);
       ksum += k[j];
       psum += v[j];
-      if (dst < a.cap) {
+      if (fits || dst < a.cap) {
         if (a.out_key) st_stream_u64<MODE>(a.out_key + dst, k[j], pol);
         if (a.out_payload) st_stream_u64<MODE>(a.out_payload + dst, v[j], pol);
         if (a.out_rowid) st_stream_u64<MODE>(a.out_rowid + dst, tbase + (size_t) j * kPbThreads + threadIdx.x, pol);
@@ -168,7 +169,8 @@ __device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePo
     kn[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_stream_u64<MODE>(p + j * kPbThreads, pol) : 0;
 }
 
-template <int KIND, bool UNIQUE, int MODE>
+// W32: the table has at most 2^32 slots / buckets, so slot arithmetic runs in 32 bits
+template <int KIND, bool UNIQUE, int MODE, bool W32>
 __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a) {
   __shared__ ProbeShared sh;
   const CachePolicy pol = make_policies();
@@ -197,11 +199,11 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
     for (int j = 0; j < kPbKeysPerThread; ++j) {
       act[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows;
       k[j] = kn[j];
-      pos[j] = murmurhash64(k[j]) & a.mask;
+      pos[j] = W32 ? (uint64_t) ((uint32_t) murmurhash64(k[j]) & (uint32_t) a.mask) : (murmurhash64(k[j]) & a.mask);
     }
     if (KIND == CC_HT_LP) {
 #pragma unroll
-      for (int j = 0; j < kPbKeysPerThread; ++j) v[j] = act[j] ? ld_table_u64<MODE>(a.slots + pos[j], pol) : kEmptyU;
+      for (int j = 0; j < kPbKeysPerThread; ++j) v[j] = act[j] ? ld_table_u64<MODE>(a.slots + (W32 ? (uint32_t) pos[j] : pos[j]), pol) : kEmptyU;
       load_tile_keys<MODE>(a, pol, ntile, nrows, kn);  // next tile's keys, behind this tile's gathers
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) act[j] = v[j] != kEmptyU;
@@ -233,8 +235,14 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
         for (int j = 0; j < kPbKeysPerThread; ++j) {
           if (act[j]) {
             if (KIND == CC_HT_LP) {
-              pos[j] = (pos[j] + 1) & a.mask;
-              v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
+              if (W32) {
+                uint32_t p32 = ((uint32_t) pos[j] + 1u) & (uint32_t) a.mask;
+                pos[j] = p32;
+                v[j] = ld_table_u64<MODE>(a.slots + p32, pol);
+              } else {
+                pos[j] = (pos[j] + 1) & a.mask;
+                v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
+              }
             } else {
               pos[j] += 1;
               act[j] = pos[j] != end[j];
@@ -297,20 +305,25 @@ __global__ void probe_finish_kernel(cc_probe_result *res, size_t cap) {
   if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = res->n_matches > cap ? 1 : 0;
 }
 
-template <int KIND, bool UNIQUE, int MODE>
-static int launch_probe(const ProbeArgs &a, cudaStream_t st) {
+template <int KIND, bool UNIQUE, int MODE, bool W32>
+static int launch_probe_w(const ProbeArgs &a, cudaStream_t st) {
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
-    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE, MODE>, kPbThreads, 0));
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE, MODE, W32>, kPbThreads, 0));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
   size_t ntiles = (a.n + kPbTile - 1) / kPbTile;
   size_t grid = (size_t) sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid == 0) grid = 1;
-  probe_batch_kernel<KIND, UNIQUE, MODE><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
+  probe_batch_kernel<KIND, UNIQUE, MODE, W32><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
   CC_CHECK_LAUNCH();
   return CC_OK;
+}
+
+template <int KIND, bool UNIQUE, int MODE>
+static int launch_probe(const ProbeArgs &a, cudaStream_t st) {
+  return a.mask <= 0xFFFFFFFFull ? launch_probe_w<KIND, UNIQUE, MODE, true>(a, st) : launch_probe_w<KIND, UNIQUE, MODE, false>(a, st);
 }
 
 template <int MODE>
@@ -334,7 +347,7 @@ static int dispatch_probe(int mode, const cc_ht *ht, const ProbeArgs &a, cudaStr
 static int g_strategy = 0;                // 0 auto, 1 direct, 2 partitioned
 static int g_mode_partitioned = 2;        // cache mode of the probe kernel behind the partition pass
 static int g_mode_direct = 0;             // cache mode of the direct probe
-static size_t g_slice_bytes = 16u << 20;  // target table bytes per partition (measured: 32 MiB slices already thrash L2)
+static size_t g_slice_bytes = 32u << 20;  // target table bytes per partition (measured sweep: profiles/r1_sweep_slices.txt)
 
 // optional live phase timing (bench.py): CUDA events on the launching stream around the three kernels
 static int g_profile = 0;
