@@ -87,13 +87,16 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t &total,
   return off;
 }
 
+// scan[L] holds up to kScanCap live lanes (a probe step may add kW lanes to kW-1 waiting ones)
+constexpr int kScanCap = 2 * kW;
+
 __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChainShared &S = *reinterpret_cast<ChainShared *>(smem_raw);
-  uint32_t *st_row = reinterpret_cast<uint32_t *>(smem_raw + sizeof(ChainShared));
-  uint32_t *st_pos = st_row + a.n_joins * kW;
-  uint32_t *st_end = st_pos + a.n_joins * kW;
-  uint32_t *bufs = st_end + a.n_joins * kW;  // chunk[L] for L = 1 .. J-1 at bufs + (L-1)*kBufCap
+  uint32_t *sc_row = reinterpret_cast<uint32_t *>(smem_raw + sizeof(ChainShared));  // [J][kScanCap]
+  uint32_t *sc_pos = sc_row + a.n_joins * kScanCap;
+  uint32_t *sc_end = sc_pos + a.n_joins * kScanCap;
+  uint32_t *bufs = sc_end + a.n_joins * kScanCap;  // chunk[L] for L = 1 .. J-1 at bufs + (L-1)*kBufCap
   const int J = a.n_joins;
   const unsigned tid = threadIdx.x;
 
@@ -106,11 +109,14 @@ __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
   __syncthreads();
 
   const size_t ntiles = (a.n_rows + kW - 1) / kW;
-  int cur = -1;
-  bool exhausted = false;
+  int cur = 0;
+  bool exhausted = false;  // no LHS tiles left (this CTA)
+  int flush_upto = 0;      // levels <= flush_upto receive no more input: their caches are drained regardless of threshold
 
-  // Probe (chaining_ht.cpp:38-58 / linear_probing_ht.cpp:39-60) for the rows handed to level L
-  auto start_scan = [&](int L, uint32_t row) {
+  // Probe (chaining_ht.cpp:38-58 / linear_probing_ht.cpp:39-60) for up to kW rows handed to level L.  Only lanes
+  // whose bucket / first slot is non-empty enter the ScanStructure, and they are APPENDED densely to the lanes already
+  // waiting there (lane refill): rounds then always run on a full set of live lanes.
+  auto probe_step = [&](int L, uint32_t row) {
     const ChainLevel &lv = a.lv[L];
     bool act = false;
     uint32_t pos = 0, end = 0;
@@ -127,84 +133,58 @@ __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
         act = ld_nc_u64(lv.slots + h) != kEmptyU;
       }
     }
-    st_row[L * kW + tid] = act ? row : kNoRow;
-    st_pos[L * kW + tid] = pos;
-    st_end[L * kW + tid] = end;
     int n_valid = __syncthreads_count(row != kNoRow);
-    int n_act = __syncthreads_count(act);
+    uint32_t total;
+    uint32_t off = block_excl_scan(act ? 1u : 0u, total, S.scan);
+    uint32_t base = S.active[L];
+    if (act) {
+      sc_row[L * kScanCap + base + off] = row;
+      sc_pos[L * kScanCap + base + off] = pos;
+      sc_end[L * kScanCap + base + off] = end;
+    }
+    __syncthreads();
     if (tid == 0) {
-      S.active[L] = (uint32_t) n_act;
+      S.active[L] = base + total;
       S.level_in[L] += (unsigned long long) n_valid;
     }
     __syncthreads();
   };
 
   for (;;) {
-    if (cur < 0) {
-      uint32_t row = kNoRow;
-      int L = 0;
-      if (!exhausted) {
-        if (tid == 0) S.tile = atomicAdd((unsigned long long *) &a.res->reserved[0], 1ull);
-        __syncthreads();
-        size_t tile = (size_t) S.tile;
-        __syncthreads();
-        if (tile < ntiles) {
-          size_t r = tile * (size_t) kW + tid;
-          row = r < a.n_rows ? (uint32_t) r : kNoRow;
-        } else {
-          exhausted = true;
-        }
-      }
-      if (exhausted) {
-        // FlushPipelineCache (main.cpp:172-191): drain the shallowest non-empty cache
-        L = 0;
-        for (int l = 1; l < J; ++l)
-          if (S.bufcnt[l] > 0) {
-            L = l;
-            break;
-          }
-        if (L == 0) break;  // every cache is empty: done
-        uint32_t cnt = S.bufcnt[L];
-        uint32_t take = cnt < (uint32_t) kW ? cnt : (uint32_t) kW;
-        row = tid < take ? bufs[(L - 1) * kBufCap + (cnt - take) + tid] : kNoRow;
-        __syncthreads();
-        if (tid == 0) S.bufcnt[L] = cnt - take;
-      }
-      start_scan(L, row);
-      cur = L;
-      continue;
-    }
-    // ---- descend: the compactor in front of level cur+1 has a chunk ready
+    // ---- 1. descend: the compactor in front of level cur+1 holds a chunk (or is being flushed)
     if (cur + 1 < J) {
       uint32_t cnt = S.bufcnt[cur + 1];
-      if (cnt >= a.lv[cur].need) {
-        uint32_t take = cnt < (uint32_t) kW ? cnt : (uint32_t) kW;
-        uint32_t row = tid < take ? bufs[cur * kBufCap + (cnt - take) + tid] : kNoRow;
-        __syncthreads();
-        if (tid == 0) S.bufcnt[cur + 1] = cnt - take;
-        start_scan(cur + 1, row);
+      const uint32_t need = (cur + 1 <= flush_upto) ? 1u : a.lv[cur].need;  // flushing: drain regardless of the threshold
+      if (cnt >= need) {
         ++cur;
         continue;
       }
     }
-    // ---- ascend: this level's scan is exhausted (HasNext() == false)
-    if (S.active[cur] == 0) {
-      --cur;
-      continue;
-    }
-    // ---- one round (Next) at level cur
-    {
+    const uint32_t n_act = S.active[cur];
+    // does level cur still have input to probe?  level 0: LHS tiles; level L: its cached chunk
+    const bool has_input = cur == 0 ? !exhausted : S.bufcnt[cur] > 0;
+    // live lanes wanted before a round: the threshold of the compactor feeding this level (1 .. kW), so that
+    // threshold 0 reproduces the uncompacted pipeline (every Next result and every probe runs as is)
+    const uint32_t want = a.lv[cur > 0 ? cur - 1 : 0].need;
+    const bool closed = cur == 0 ? exhausted : cur <= flush_upto;  // this level will receive no further input
+    // ---- 2. round (Next) when enough live lanes wait, or when nothing more can ever be added.  Too few lanes
+    //         and an open upstream: the lanes simply wait in the scan (step 4 ascends) until more rows arrive.
+    if (n_act >= want || (n_act > 0 && !has_input && closed)) {
       const int L = cur;
       const ChainLevel &lv = a.lv[L];
-      uint32_t row = st_row[L * kW + tid];
+      const uint32_t first = n_act > (uint32_t) kW ? n_act - kW : 0;  // the last <= kW lanes are processed
+      const uint32_t lanes = n_act - first;
+      uint32_t row = kNoRow, p = 0, e = 0;
+      if (tid < lanes) {
+        row = sc_row[L * kScanCap + first + tid];
+        p = sc_pos[L * kScanCap + first + tid];
+        e = sc_end[L * kScanCap + first + tid];
+      }
       uint32_t m = 0;
       bool still = false;
-      uint64_t key = 0;
       if (row != kNoRow) {
-        key = (uint64_t) __ldg(lv.col + row);
-        uint32_t p = st_pos[L * kW + tid];
+        uint64_t key = (uint64_t) __ldg(lv.col + row);
         if (lv.kind == CC_HT_CHAIN) {
-          uint32_t e = st_end[L * kW + tid];
           uint64_t v[kS];
 #pragma unroll
           for (int s = 0; s < kS; ++s) v[s] = (p + s < e) ? (uint64_t) __ldg(lv.ckeys + p + s) : ~key;
@@ -229,10 +209,16 @@ __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
           p = (uint32_t) ((uint64_t) (p + kS) & lv.mask);
         }
         if (lv.unique && m) still = false;
-        st_pos[L * kW + tid] = p;
-        if (!still) st_row[L * kW + tid] = kNoRow;
       }
-      int n_lanes = __syncthreads_count(row != kNoRow);
+      __syncthreads();  // every lane has read its scan entry: the tail may be rewritten
+      // AdvancePointers: surviving lanes stay in the scan, compacted in place at the tail
+      uint32_t n_still;
+      uint32_t soff = block_excl_scan(still ? 1u : 0u, n_still, S.scan);
+      if (still) {
+        sc_row[L * kScanCap + first + soff] = row;
+        sc_pos[L * kScanCap + first + soff] = p;
+        sc_end[L * kScanCap + first + soff] = e;
+      }
       uint32_t total;
       uint32_t off = block_excl_scan(m, total, S.scan);
       if (L + 1 < J) {
@@ -271,13 +257,56 @@ __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
           }
         }
       }
-      int n_still = __syncthreads_count(still);
+      __syncthreads();
       if (tid == 0) {
-        S.active[L] = (uint32_t) n_still;
+        S.active[L] = first + n_still;
         S.steps[L] += 1;
-        S.lanes[L] += (unsigned long long) n_lanes;
+        S.lanes[L] += (unsigned long long) lanes;
       }
       __syncthreads();
+      continue;
+    }
+    // ---- 3. probe step: refill the scan of level cur from its input
+    if (has_input) {
+      uint32_t row = kNoRow;
+      if (cur == 0) {
+        if (tid == 0) S.tile = atomicAdd((unsigned long long *) &a.res->reserved[0], 1ull);
+        __syncthreads();
+        size_t tile = (size_t) S.tile;
+        __syncthreads();
+        if (tile < ntiles) {
+          size_t r = tile * (size_t) kW + tid;
+          row = r < a.n_rows ? (uint32_t) r : kNoRow;
+        } else {
+          exhausted = true;
+          continue;
+        }
+      } else {
+        uint32_t cnt = S.bufcnt[cur];
+        uint32_t take = cnt < (uint32_t) kW ? cnt : (uint32_t) kW;
+        row = tid < take ? bufs[(cur - 1) * kBufCap + (cnt - take) + tid] : kNoRow;
+        __syncthreads();
+        if (tid == 0) S.bufcnt[cur] = cnt - take;
+      }
+      probe_step(cur, row);
+      continue;
+    }
+    // ---- 4. level cur has no input (and no lanes, or too few while its upstream can still deliver)
+    if (cur > 0) {
+      --cur;  // ascend: back to the producer of this level's input
+      continue;
+    }
+    // level 0 idle and the table exhausted: FlushPipelineCache (main.cpp:172-191) -- drain the caches top-down
+    {
+      int next = 0;
+      for (int l = 1; l < J; ++l)
+        if (S.bufcnt[l] > 0 || S.active[l] > 0) {
+          next = l;
+          break;
+        }
+      if (next == 0) break;  // everything drained
+      flush_upto = next;     // levels <= next get no new input any more
+      cur = next;
     }
   }
 
@@ -352,7 +381,7 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
   chain_init_kernel<<<1, 32, 0, st>>>(d_result);
   CC_CHECK_LAUNCH();
   if (n_rows) {
-    size_t smem = sizeof(ChainShared) + n_joins * 3 * kW * sizeof(uint32_t) + (n_joins - 1) * (size_t) kBufCap * sizeof(uint32_t);
+    size_t smem = sizeof(ChainShared) + n_joins * 3 * (size_t) kScanCap * sizeof(uint32_t) + (n_joins - 1) * (size_t) kBufCap * sizeof(uint32_t);
     CC_CUDA(cudaFuncSetAttribute(chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0;
     CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_fused_kernel, kW, smem));
