@@ -261,28 +261,79 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
       }
       emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
     } else {
-      // ---- rounds: one Next() each (ScanInnerJoin + GatherResult + AdvancePointers)
+      // ---- tables with duplicate keys: a lane keeps walking past its matches (linear_probing_ht.cpp:101-109).
+      // One round = up to kRoundEntries Next() steps of every live key at once: the thread loads the next entries of
+      // a key together (one or two sectors), records WHICH of them match (the payload of a match is the key itself,
+      // chaining_ht.cpp:34 stores keys only), the CTA ranks the per-thread match counts with one exclusive scan,
+      // reserves the output range with one atomicAdd and every thread stores its rows at consecutive positions.
+      constexpr int kRoundEntries = KIND == CC_HT_CHAIN ? 8 : 4;
       bool any;
       do {
-        bool m[kPbKeysPerThread];
-#pragma unroll
-        for (int j = 0; j < kPbKeysPerThread; ++j) m[j] = act[j] && (v[j] == k[j]);
-        emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
+        uint32_t mm[kPbKeysPerThread];
+        uint32_t cnt = 0;
         bool mine = false;
 #pragma unroll
         for (int j = 0; j < kPbKeysPerThread; ++j) {
+          mm[j] = 0;
           if (act[j]) {
-            if (KIND == CC_HT_LP) {
-              pos[j] = (pos[j] + 1) & a.mask;
-              v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
-              act[j] = v[j] != kEmptyU;
-            } else {
-              pos[j] += 1;
+            uint64_t e[kRoundEntries];
+            if (KIND == CC_HT_CHAIN) {
+#pragma unroll
+              for (int q = 0; q < kRoundEntries; ++q)
+                e[q] = (uint32_t) pos[j] + q < end[j] ? ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j] + q, pol) : ~k[j];
+#pragma unroll
+              for (int q = 0; q < kRoundEntries; ++q) mm[j] |= ((uint32_t) pos[j] + q < end[j] && e[q] == k[j]) ? (1u << q) : 0u;
+              pos[j] = end[j] - (uint32_t) pos[j] > (uint32_t) kRoundEntries ? pos[j] + kRoundEntries : (uint64_t) end[j];
               act[j] = pos[j] != end[j];
-              if (act[j]) v[j] = ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol);
+            } else {
+              e[0] = v[j];  // the current slot was already fetched
+#pragma unroll
+              for (int q = 1; q < kRoundEntries; ++q) e[q] = ld_table_u64<MODE>(a.slots + ((pos[j] + q) & a.mask), pol);
+              bool open = true;
+#pragma unroll
+              for (int q = 0; q < kRoundEntries; ++q) {
+                open = open && e[q] != kEmptyU;  // the walk ends at the first empty slot
+                mm[j] |= (open && e[q] == k[j]) ? (1u << q) : 0u;
+              }
+              pos[j] = (pos[j] + kRoundEntries) & a.mask;
+              act[j] = open;
+              if (open) {
+                v[j] = ld_table_u64<MODE>(a.slots + pos[j], pol);
+                act[j] = v[j] != kEmptyU;
+              }
             }
+            cnt += __popc(mm[j]);
           }
           mine |= act[j];
+        }
+        // rank: exclusive scan of the per-thread match counts over the CTA
+        uint32_t incl = warp_incl_scan_u32(cnt);
+        const unsigned w = threadIdx.x >> 5;
+        if (lane_id() == 31) sh.cnt[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+          uint32_t c = lane_id() < kPbWarps ? sh.cnt[lane_id()] : 0;
+          uint32_t ci = warp_incl_scan_u32(c);
+          sh.cnt[lane_id()] = ci - c;
+          if (lane_id() == 31) sh.base = ci ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) ci) : 0ull;
+        }
+        __syncthreads();
+        uint64_t dst = sh.base + sh.cnt[w] + (incl - cnt);
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) {
+          uint32_t bits = mm[j];
+          const uint32_t c = __popc(bits);
+          ksum += k[j] * c;
+          psum += k[j] * c;  // payload of a match == the matched build key == the probe key
+          while (bits) {
+            bits &= bits - 1;
+            if (dst < a.cap) {
+              if (a.out_key) st_stream_u64<MODE>(a.out_key + dst, k[j], pol);
+              if (a.out_payload) st_stream_u64<MODE>(a.out_payload + dst, k[j], pol);
+              if (a.out_rowid) st_stream_u64<MODE>(a.out_rowid + dst, tbase + (size_t) j * kPbThreads + threadIdx.x, pol);
+            }
+            ++dst;
+          }
         }
         any = __syncthreads_or(mine);
       } while (any);
