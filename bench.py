@@ -194,6 +194,7 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sub-batches", type=int, default=1, help="N>1 with p2p: shuffle of sub-batch b+1 overlaps the probe of sub-batch b")
+    ap.add_argument("--peer-blocks", type=int, default=0, help="N>1 with p2p: CTA cap of the NVLink-bound peer scatter (0 = all SMs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory scatter or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "ours":
@@ -236,7 +237,7 @@ def main() -> int:
         key_space = n_build * world
         local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
         join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
-                                   capacity_rows=int(n_probe * 1.05) + (1 << 20))
+                                   capacity_rows=int(n_probe * 1.05) + (1 << 20), peer_blocks=args.peer_blocks)
         table = join.table
         del local_build
     torch.cuda.synchronize()

@@ -143,6 +143,7 @@ SIGNATURES = {
     "cc_partition_count": (_int, [_vp, _sz, _int, _vp, _vp]),
     "cc_partition_scatter": (_int, [_vp, _sz, _int, _vp, _vp, _vp, _vp]),
     "cc_partition_scatter_peers": (_int, [_vp, _sz, _int, _vp, _vp, _pvp, _vp]),
+    "cc_partition_set_peer_blocks": (_int, [_int]),
     "cc_ipc_export": (_int, [_vp, _vp]),
     "cc_ipc_open": (_int, [_vp, _pvp]),
     "cc_ipc_close": (_int, [_vp]),

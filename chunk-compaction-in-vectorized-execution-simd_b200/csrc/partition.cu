@@ -111,29 +111,33 @@ __global__ void __launch_bounds__(kPartThreads)
     uint32_t p[kPartItems], r[kPartItems];
     const size_t tbase = tile * (size_t) kPartTile;
     const uint32_t tile_n = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);  // CTA-uniform
-    if (TMA && tile < nfull) {
+    const bool staged = TMA && tile < nfull;
+    if (staged) {
       mbar_wait(&s_bar, phase);
       phase ^= 1u;
 #pragma unroll
       for (int j = 0; j < kPartItems; ++j) k[j] = s_in[j * kPartThreads + threadIdx.x];
-      __syncthreads();  // every thread holds its keys (and s_cnt is cleared): the buffer may be refilled
-      if (threadIdx.x == 0 && tile + gridDim.x < nfull) {
-        mbar_expect_tx(&s_bar, kPartTile * 8);
-        tma_load_1d(s_in, keys + (tile + gridDim.x) * (size_t) kPartTile, kPartTile * 8, &s_bar);
-      }
     } else {
-      __syncthreads();
       const int64_t *src = keys + tbase + threadIdx.x;
 #pragma unroll
       for (int j = 0; j < kPartItems; ++j) k[j] = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n ? (uint64_t) __ldg(src + j * kPartThreads) : 0;
     }
+    __syncthreads();  // s_cnt is cleared (loop top)
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
       bool ok = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n;
       p[j] = ok ? fn(k[j]) : 0xFFFFFFFFu;
       r[j] = ok ? atomicAdd(&s_cnt[p[j]], 1u) : 0;
     }
+    // Every thread has now CONSUMED its keys (hashed them), so its reads of the staging buffer are complete.
+    // The refill is an async-proxy write: it must be ordered after these generic-proxy reads with a proxy fence
+    // -- bar.sync alone is not enough (observed: whole 32-key warp slices replaced by the next tile's keys).
+    if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (TMA && threadIdx.x == 0 && tile + gridDim.x < nfull) {
+      mbar_expect_tx(&s_bar, kPartTile * 8);
+      tma_load_1d(s_in, keys + (tile + gridDim.x) * (size_t) kPartTile, kPartTile * 8, &s_bar);
+    }
     // exclusive scan of the per-partition counts (parts <= kMaxParts = kBins * kPartThreads).  The global
     // range reservations (one atomicAdd per non-empty partition) are ISSUED here but only consumed after the
     // shared-memory sort below, so their L2 round trip overlaps that phase instead of stalling the CTA.
@@ -264,6 +268,14 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
                                blocks, as_stream(s));
 }
 
+static int g_peer_blocks = 0;  // 0 = fill the GPU; > 0 = CTA cap of the peer scatter (it is NVLink-bound)
+
+int cc_partition_set_peer_blocks(int blocks) {
+  CC_REQUIRE(blocks >= 0, "blocks must be >= 0");
+  g_peer_blocks = blocks;
+  return CC_OK;
+}
+
 int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_base, uint64_t *d_cursors,
                                int64_t *const *h_peer_bufs, cc_stream_t s) {
   CC_TRY(require_device());
@@ -278,6 +290,7 @@ int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, 
   CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(uint64_t), as_stream(s)));
   if (n == 0) return CC_OK;
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
+  if (g_peer_blocks > 0 && blocks > (size_t) g_peer_blocks) blocks = (size_t) g_peer_blocks;
   return launch_scatter<true>(d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_base, (unsigned long long *) d_cursors, dst,
                               blocks, as_stream(s));
 }

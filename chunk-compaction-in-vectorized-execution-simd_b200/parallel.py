@@ -68,7 +68,7 @@ class PeerExchange:
     consecutive shuffles so that a fast rank can already scatter step i+1 while a slow one still
     probes step i."""
 
-    def __init__(self, pkg, capacity_rows: int, group=None, n_buffers: int = 3):
+    def __init__(self, pkg, capacity_rows: int, group=None, n_buffers: int = 3, peer_blocks: int = 0):
         import ctypes as C
 
         self.pkg, self.group = pkg, group
@@ -76,6 +76,7 @@ class PeerExchange:
         self.log2p = log2_exact(self.world)
         self.capacity = int(capacity_rows)
         self.n_buffers = n_buffers
+        pkg._lib.check(pkg.lib().cc_partition_set_peer_blocks(int(peer_blocks)))
         self.step = 0
         lib = pkg.lib()
         self.local, self.peers, self._opened = [], [], []
@@ -144,7 +145,7 @@ class PartitionedJoin:
     """Build once, probe many times.  `pkg` is the product package (passed in to avoid a circular import)."""
 
     def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition",
-                 exchange: str = "nccl", capacity_rows: int = 0):
+                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0):
         """plan: "partition" (hash-partition both sides) or "broadcast" (replicate the build side).
         exchange: "nccl" (scatter locally, then all_to_all_single) or "p2p" (PeerExchange: the scatter kernel
         writes into the owners' buffers over NVLink); capacity_rows sizes the p2p receive buffers."""
@@ -154,7 +155,7 @@ class PartitionedJoin:
         self.rank = dist.get_rank(group)
         self.log2p = log2_exact(self.world)
         self.plan = plan
-        self.peer = PeerExchange(pkg, capacity_rows, group) if (exchange == "p2p" and plan == "partition") else None
+        self.peer = PeerExchange(pkg, capacity_rows, group, peer_blocks=peer_blocks) if (exchange == "p2p" and plan == "partition") else None
         T = pkg.LPHashTable if kind == pkg.CC_HT_LP else pkg.HashTable
         if plan == "broadcast":
             n_local = torch.tensor([local_build_keys.numel()], dtype=torch.int64, device=local_build_keys.device)

@@ -311,6 +311,9 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
  * readers with a stream-ordered collective (e.g. an all-reduce), see parallel.py.               */
 int cc_partition_scatter_peers(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_base,
                                uint64_t *d_cursors, int64_t *const *h_peer_bufs, cc_stream_t stream);
+/* CTA cap of cc_partition_scatter_peers (0 = fill the GPU).  The peer scatter is NVLink-bound, so a few dozen
+ * CTAs saturate the links and leave the other SMs to a probe kernel running on another stream.  */
+int cc_partition_set_peer_blocks(int blocks);
 /* CUDA IPC plumbing for one-process-per-GPU peers (the pointer must come from cc_malloc). */
 typedef struct {
   unsigned char bytes[64];

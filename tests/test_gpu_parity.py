@@ -458,10 +458,13 @@ def test_chain_execute_edge_cases(ccb):
 
 
 # ------------------------------------------------------------------ partitioning
-@pytest.mark.parametrize("log2p", [0, 1, 3, 8])
-def test_partition_kernels(ccb, log2p):
+@pytest.mark.parametrize("log2p,n,sequential", [(0, 333333, False), (1, 333333, False), (3, 333333, False), (8, 333333, False),
+                                                 (0, 3 << 22, True), (4, (3 << 22) + 4099, True), (9, 1 << 24, False)])
+def test_partition_kernels(ccb, log2p, n, sequential):
+    """Many tiles per CTA (the TMA refill path of the scatter kernel) and sequential keys included: an early version lost
+    whole warp slices of a tile when the async refill raced with the reads of the staging buffer."""
     rng = np.random.Generator(np.random.PCG64(log2p))
-    keys = rng.integers(-(1 << 62), 1 << 62, size=333333, dtype=np.int64)
+    keys = np.arange(n, dtype=np.int64) if sequential else rng.integers(-(1 << 62), 1 << 62, size=n, dtype=np.int64)
     out, counts, offsets = ccb.partition_keys(dev(keys), log2p)
     out = out.cpu().numpy()
     P = 1 << log2p
@@ -498,3 +501,34 @@ def test_chain_execute_tuned_negative_feedback(ccb):
     got = torch.stack([c[: r["n_tuples"]] for c in r["out_cols"]], dim=1).cpu().numpy()
     want = O.pipeline([O.OracleChain(O.build_keys(rhs, cf)) for _ in range(J)], lhs, 256, collect=True)
     assert r["overflow"] == 0 and np.array_equal(G.sort_rows(got), G.sort_rows(want["tuples"]))
+
+
+@pytest.mark.parametrize("log2p,n", [(0, 3 << 22), (1, 3 << 22), (3, (3 << 20) + 12345), (2, 333333)])
+def test_partition_scatter_peers(ccb, log2p, n):
+    """cc_partition_scatter_peers: partition p lands in its own destination buffer (peer memory in production),
+    at the base offset handed in, complete and uncorrupted -- many tiles per CTA (TMA refill path) and ragged tails."""
+    import ctypes as C
+
+    rng = np.random.Generator(np.random.PCG64(n + log2p))
+    keys = rng.integers(-(1 << 62), 1 << 62, size=n, dtype=np.int64)
+    P = 1 << log2p
+    pid = (O.murmurhash64(keys.view(np.uint64)) >> np.uint64(64 - log2p)).astype(np.int64) if log2p else np.zeros(n, dtype=np.int64)
+    counts = np.bincount(pid, minlength=P)
+    base = np.arange(P, dtype=np.int64) * 7 + 3  # arbitrary start row of this sender inside every destination buffer
+    bufs = [torch.full((int(counts[p] + base[p]) + 16,), -7, dtype=torch.int64, device="cuda") for p in range(P)]
+    dkeys = dev(keys)
+    dbase = dev(base)
+    cursors = torch.zeros(P, dtype=torch.int64, device="cuda")
+    ptrs = (C.c_void_p * P)(*[b.data_ptr() for b in bufs])
+    for blocks in (0, 8):
+        ccb._lib.check(ccb.lib().cc_partition_set_peer_blocks(blocks))
+        for b in bufs:
+            b.fill_(-7)
+        ccb._lib.check(ccb.lib().cc_partition_scatter_peers(dkeys.data_ptr(), n, log2p, dbase.data_ptr(), cursors.data_ptr(), ptrs,
+                                                            torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        for p in range(P):
+            got = bufs[p].cpu().numpy()
+            assert np.all(got[: base[p]] == -7) and np.all(got[base[p] + counts[p]:] == -7)
+            assert np.array_equal(np.sort(got[base[p]: base[p] + counts[p]]), np.sort(keys[pid == p])), (p, blocks)
+    ccb._lib.check(ccb.lib().cc_partition_set_peer_blocks(0))
