@@ -22,9 +22,11 @@
 
 namespace ccb {
 
+// gate (optional): the kernel only runs when *gate != 0 (device-side fallback switch, see partition_single_device)
 __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn,
-                                                                       unsigned long long *counts) {
+                                                                       unsigned long long *counts, const int *gate) {
   __shared__ uint32_t s_cnt[kMaxParts];
+  if (gate && *gate == 0) return;
   const int parts = (int) fn.pmask + 1;
   for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
   __syncthreads();
@@ -47,8 +49,9 @@ __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int
 
 // exclusive scan of the P counters (single CTA), also resets the cursors
 __global__ void partition_offsets_kernel(const unsigned long long *__restrict__ counts, int parts, unsigned long long *offsets,
-                                         unsigned long long *cursors) {
+                                         unsigned long long *cursors, const int *gate) {
   __shared__ unsigned long long s[kMaxParts];
+  if (gate && *gate == 0) return;
   for (int i = threadIdx.x; i < parts; i += blockDim.x) s[i] = counts[i];
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -80,7 +83,11 @@ struct ScatterDst {
 template <bool PEERS, bool TMA>
 __global__ void __launch_bounds__(kPartThreads)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
-                             unsigned long long *cursors, ScatterDst dst) {
+                             unsigned long long *cursors, ScatterDst dst, unsigned long long cap_rows, int *flag, int gated) {
+  // cap_rows > 0 (single-pass mode): partition p owns the fixed region [p * cap_rows, (p + 1) * cap_rows) of the output, no
+  //   histogram pass needed; a tile that would overrun a region raises *flag and drops that run (the gated two-pass
+  //   fallback then redoes the whole partition).  gated: run only if *flag != 0.
+  if (gated && *flag == 0) return;
   extern __shared__ __align__(128) unsigned char s_dyn[];
   uint64_t *s_sorted = reinterpret_cast<uint64_t *>(s_dyn);                  // [kPartTile]
   uint64_t *s_in = s_sorted + kPartTile;                                       // [kPartTile] (TMA only)
@@ -165,7 +172,19 @@ __global__ void __launch_bounds__(kPartThreads)
         gbase[q] = 0;
         if (i < parts) {
           s_off[i] = (uint16_t) run;
-          if (c[q]) gbase[q] = offsets[i] + atomicAdd(cursors + i, (unsigned long long) c[q]);
+          if (c[q]) {
+            unsigned long long at = atomicAdd(cursors + i, (unsigned long long) c[q]);
+            if (cap_rows) {
+              if (at + c[q] > cap_rows) {
+                atomicOr(flag, 1);
+                gbase[q] = ~0ull;  // overrun: this run is dropped
+              } else {
+                gbase[q] = (unsigned long long) i * cap_rows + at;
+              }
+            } else {
+              gbase[q] = offsets[i] + at;
+            }
+          }
         }
         run += c[q];
       }
@@ -181,13 +200,14 @@ __global__ void __launch_bounds__(kPartThreads)
 #pragma unroll
     for (int q = 0; q < kBins; ++q) {
       int i = threadIdx.x * kBins + q;
-      if (i < parts) s_delta[i] = gbase[q] - first[q];
+      if (i < parts) s_delta[i] = gbase[q] == ~0ull ? ~0ull : gbase[q] - first[q];
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
       uint32_t pp = s_part[i];
       int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
-      out[s_delta[pp] + i] = (int64_t) s_sorted[i];
+      unsigned long long d = s_delta[pp];
+      if (d != ~0ull) out[d + i] = (int64_t) s_sorted[i];
     }
     __syncthreads();
   }
@@ -195,31 +215,69 @@ __global__ void __launch_bounds__(kPartThreads)
 
 template <bool PEERS>
 static int launch_scatter(const int64_t *d_keys, size_t n, PartFn fn, const unsigned long long *d_offsets, unsigned long long *d_cursors,
-                          const ScatterDst &dst, size_t blocks, cudaStream_t st) {
+                          const ScatterDst &dst, size_t blocks, cudaStream_t st, unsigned long long cap_rows = 0, int *flag = nullptr,
+                          int gated = 0) {
   const bool tma = (reinterpret_cast<uintptr_t>(d_keys) & 15) == 0;  // bulk copies need 16-byte alignment
   const size_t smem = (tma ? 2 : 1) * (size_t) kPartTile * sizeof(uint64_t) + (size_t) kPartTile * sizeof(uint16_t);
   if (tma) {
     CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst);
+    partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated);
   } else {
     CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    partition_scatter_kernel<PEERS, false><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst);
+    partition_scatter_kernel<PEERS, false><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated);
   }
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
 
+// tiles of kSegTile rows per partition region (single-pass mode): prefix[p] = first tile of partition p, prefix[parts] = total
+__global__ void partition_seg_prefix_kernel(const unsigned long long *__restrict__ cursors, int parts, unsigned long long cap_rows,
+                                            uint32_t seg_tile, uint32_t *prefix) {
+  __shared__ uint32_t s[kMaxParts];
+  for (int i = threadIdx.x; i < parts; i += blockDim.x) {
+    unsigned long long c = cursors[i] < cap_rows ? cursors[i] : cap_rows;
+    s[i] = (uint32_t) ((c + seg_tile - 1) / seg_tile);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < parts; ++i) {
+      uint32_t c = s[i];
+      s[i] = run;
+      run += c;
+    }
+    prefix[parts] = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < parts; i += blockDim.x) prefix[i] = s[i];
+}
+
+int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
+                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st) {
+  const int parts = (int) fn.pmask + 1;
+  CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
+  CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
+  if (blocks == 0) blocks = 1;
+  ScatterDst dst;
+  dst.p[0] = d_out;
+  CC_TRY(launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0));
+  partition_seg_prefix_kernel<<<1, 256, 0, st>>>(d_cursors, parts, cap_rows, seg_tile, d_prefix);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
-                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count) {
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count, int *gate) {
   const int parts = (int) fn.pmask + 1;
   CC_CUDA(cudaMemsetAsync(d_counts, 0, parts * sizeof(unsigned long long), st));
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   if (blocks == 0) blocks = 1;
   if (n) {
-    partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_counts);
+    partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_counts, gate);
     CC_CHECK_LAUNCH();
   }
-  partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors);
+  partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors, gate);
   CC_CHECK_LAUNCH();
   if (after_count) {
     if (!*after_count) cudaEventCreate(after_count);
@@ -228,7 +286,7 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
   if (n) {
     ScatterDst dst;
     dst.p[0] = d_out;
-    CC_TRY(launch_scatter<false>(d_keys, n, fn, d_offsets, d_cursors, dst, blocks, st));
+    CC_TRY(launch_scatter<false>(d_keys, n, fn, d_offsets, d_cursors, dst, blocks, st, 0, gate, gate ? 1 : 0));
   }
   return CC_OK;
 }
@@ -248,7 +306,7 @@ int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t
   if (n == 0) return CC_OK;
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(d_keys, n, PartFn::high_bits(log2_parts),
-                                                                              (unsigned long long *) d_counts);
+                                                                              (unsigned long long *) d_counts, nullptr);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

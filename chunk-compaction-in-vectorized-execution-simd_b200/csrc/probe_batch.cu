@@ -59,6 +59,14 @@ struct ProbeArgs {
   size_t cap;
   cc_probe_result *res;
   unsigned long long *tile_counter;  // zero-initialised per launch
+  // segmented key column (behind the single-pass partition): partition p owns rows [p * seg_cap, p * seg_cap + seg_cursors[p]);
+  // seg_prefix[0 .. seg_parts] = exclusive prefix of the per-partition tile counts.  seg_parts == 0: plain dense column.
+  const uint32_t *seg_prefix;
+  const unsigned long long *seg_cursors;
+  unsigned long long seg_cap;
+  int seg_parts;
+  const int *gate;  // optional device-side switch: run only if (*gate != 0) == gate_want
+  int gate_want;
 };
 
 // Cache mode HINT (MODE bit 1): L2 eviction priorities (createpolicy + L2::cache_hint) -- the
@@ -111,8 +119,42 @@ __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v, const CachePo
 struct ProbeShared {
   uint32_t cnt[32];
   unsigned long long base;
-  unsigned long long tile_a, tile_b;  // tile indices handed out by the global counter
+  unsigned long long off_a, off_b;  // first row of the tiles handed out by the global counter
+  uint32_t rows_a, rows_b;          // their row counts (0 = no such tile)
 };
+
+// thread 0: translate a global tile index into (first row, row count); false = past the last tile.
+// Segmented mode: every partition region holds a whole number T = seg_cap / kPbTile of tiles, so the mapping is one
+// division and one shared-memory read; tiles beyond a region's fill have rows == 0 and are skipped by the caller.
+__device__ __forceinline__ bool tile_lookup(const ProbeArgs &a, const ProbeShared &sh, unsigned long long g, unsigned long long &off,
+                                            uint32_t &rows) {
+  off = 0;
+  rows = 0;
+  if (a.seg_parts == 0) {
+    const unsigned long long ntiles = (a.n + kPbTile - 1) / kPbTile;
+    if (g >= ntiles) return false;
+    off = g * (unsigned long long) kPbTile;
+    rows = (uint32_t) (a.n - off < (unsigned long long) kPbTile ? a.n - off : (unsigned long long) kPbTile);
+    return true;
+  }
+  const uint32_t T = (uint32_t) (a.seg_cap / kPbTile);
+  if (g >= (unsigned long long) T * (unsigned long long) a.seg_parts) return false;
+  const uint32_t p = (uint32_t) g / T, local = (uint32_t) g - p * T;
+  const unsigned long long first = (unsigned long long) local * kPbTile;
+  // region fill count through the read-only L1 path (the same few regions are asked for again and again); a shared-memory
+  // copy would grow the carve-out, which costs this chip gather throughput
+  unsigned long long cnt = __ldg(a.seg_cursors + p);
+  if (cnt > a.seg_cap) cnt = a.seg_cap;
+  off = (unsigned long long) p * a.seg_cap + first;
+  rows = cnt > first ? (uint32_t) (cnt - first < (unsigned long long) kPbTile ? cnt - first : (unsigned long long) kPbTile) : 0u;
+  return true;
+}
+
+// thread 0: next non-empty tile from the global counter (rows == 0: none left).  `g` is an index already requested.
+__device__ __forceinline__ void tile_fetch(const ProbeArgs &a, const ProbeShared &sh, unsigned long long g, unsigned long long &off,
+                                           uint32_t &rows) {
+  while (tile_lookup(a, sh, g, off, rows) && rows == 0) g = atomicAdd(a.tile_counter, 1ull);
+}
 
 // Compaction step: rank the matches of the CTA, reserve a contiguous range of the global output
 // with ONE atomicAdd and store key / payload / row id at consecutive positions.
@@ -153,17 +195,10 @@ __device__ __forceinline__ void emit_matches(const ProbeArgs &a, ProbeShared &sh
   }
 }
 
-// rows of tile `tile` that exist (0 .. kPbTile): the only 64-bit bounds arithmetic per tile, CTA-uniform
-__device__ __forceinline__ uint32_t tile_rows(size_t tile, size_t ntiles, size_t n) {
-  if (tile >= ntiles) return 0;
-  size_t rem = n - tile * (size_t) kPbTile;
-  return rem < (size_t) kPbTile ? (uint32_t) rem : (uint32_t) kPbTile;
-}
-
 template <int MODE>
-__device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, size_t tile, uint32_t rows,
+__device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, unsigned long long off, uint32_t rows,
                                                uint64_t (&kn)[kPbKeysPerThread]) {
-  const int64_t *p = a.keys + tile * (size_t) kPbTile + threadIdx.x;
+  const int64_t *p = a.keys + off + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < kPbKeysPerThread; ++j)
     kn[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_stream_u64<MODE>(p + j * kPbThreads, pol) : 0;
@@ -175,22 +210,25 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
   __shared__ ProbeShared sh;
   const CachePolicy pol = make_policies();
   uint64_t ksum = 0, psum = 0;
-  const size_t ntiles = (a.n + kPbTile - 1) / kPbTile;
-  // dynamic tile scheduling: `tile` is being processed, the keys of `ntile` are in flight, and
-  // thread 0 fetches the index after that while the CTA works (published through the emit barriers)
+  if (a.gate && ((*a.gate != 0) != (a.gate_want != 0))) return;  // device-side strategy switch (CTA-uniform)
+  // dynamic tile scheduling: one tile is being processed, the keys of the next are in flight, and thread 0
+  // fetches the one after that while the CTA works (published through the emit barriers)
   if (threadIdx.x == 0) {
-    sh.tile_a = atomicAdd(a.tile_counter, 1ull);
-    sh.tile_b = atomicAdd(a.tile_counter, 1ull);
+    tile_fetch(a, sh, atomicAdd(a.tile_counter, 1ull), sh.off_a, sh.rows_a);
+    tile_fetch(a, sh, atomicAdd(a.tile_counter, 1ull), sh.off_b, sh.rows_b);
   }
   __syncthreads();
-  size_t tile = (size_t) sh.tile_a, ntile = (size_t) sh.tile_b;
+  unsigned long long off = sh.off_a, noff = sh.off_b;
+  uint32_t rows = sh.rows_a, nrows = sh.rows_b;
   __syncthreads();
   uint64_t kn[kPbKeysPerThread];
-  uint32_t rows = tile_rows(tile, ntiles, a.n);
-  load_tile_keys<MODE>(a, pol, tile, rows, kn);
-  while (tile < ntiles) {
-    const size_t tbase = tile * (size_t) kPbTile;
-    const uint32_t nrows = tile_rows(ntile, ntiles, a.n);
+  load_tile_keys<MODE>(a, pol, off, rows, kn);
+  while (rows > 0) {
+    const size_t tbase = (size_t) off;
+    // thread 0 requests the tile after next NOW and translates / publishes it just before the emit barriers, so the
+    // atomic's L2 round trip is off warp 0's path to the barrier
+    unsigned long long g_after = 0;
+    if (threadIdx.x == 0) g_after = atomicAdd(a.tile_counter, 1ull);
     uint64_t k[kPbKeysPerThread], v[kPbKeysPerThread], pos[kPbKeysPerThread];
     uint32_t end[kPbKeysPerThread];
     bool act[kPbKeysPerThread];
@@ -204,14 +242,14 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
     if (KIND == CC_HT_LP) {
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) v[j] = act[j] ? ld_table_u64<MODE>(a.slots + (W32 ? (uint32_t) pos[j] : pos[j]), pol) : kEmptyU;
-      load_tile_keys<MODE>(a, pol, ntile, nrows, kn);  // next tile's keys, behind this tile's gathers
+      load_tile_keys<MODE>(a, pol, noff, nrows, kn);  // next tile's keys, behind this tile's gathers
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) act[j] = v[j] != kEmptyU;
     } else {
       uint2 d[kPbKeysPerThread];
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) d[j] = act[j] ? ld_table_u32x2<MODE>(a.dir + pos[j], pol) : make_uint2(0, 0);
-      load_tile_keys<MODE>(a, pol, ntile, nrows, kn);
+      load_tile_keys<MODE>(a, pol, noff, nrows, kn);
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
         pos[j] = d[j].x;
@@ -220,7 +258,6 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
         v[j] = act[j] ? ld_table_u64<MODE>((const uint64_t *) a.ckeys + pos[j], pol) : 0;
       }
     }
-    if (threadIdx.x == 0) sh.tile_a = atomicAdd(a.tile_counter, 1ull);  // index for the iteration after next
     if (UNIQUE) {
       // walk all of the thread's probe sequences / chains together: one dependent load per lap for
       // every key that has neither matched nor run out, instead of finishing key 0 before key 1
@@ -259,6 +296,7 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
           }
         }
       }
+      if (threadIdx.x == 0) tile_fetch(a, sh, g_after, sh.off_a, sh.rows_a);
       emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
     } else {
       // ---- tables with duplicate keys: a lane keeps walking past its matches (linear_probing_ht.cpp:101-109).
@@ -267,6 +305,7 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
       // chaining_ht.cpp:34 stores keys only), the CTA ranks the per-thread match counts with one exclusive scan,
       // reserves the output range with one atomicAdd and every thread stores its rows at consecutive positions.
       constexpr int kRoundEntries = KIND == CC_HT_CHAIN ? 8 : 4;
+      if (threadIdx.x == 0) tile_fetch(a, sh, g_after, sh.off_a, sh.rows_a);  // published by the barriers of the first round
       bool any;
       do {
         uint32_t mm[kPbKeysPerThread];
@@ -338,11 +377,12 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
         any = __syncthreads_or(mine);
       } while (any);
     }
-    // sh.tile_a was written before the barriers inside emit_matches: visible to everyone now
-    tile = ntile;
+    // sh.off_a / rows_a were written before the barriers inside the emit: visible to everyone now
+    off = noff;
     rows = nrows;
-    ntile = (size_t) sh.tile_a;
-    __syncthreads();  // protects sh.tile_a / sh.cnt / sh.base against the next iteration
+    noff = sh.off_a;
+    nrows = sh.rows_a;
+    __syncthreads();  // protects sh.off_a / sh.cnt / sh.base against the next iteration
   }
   ksum = warp_sum_u64(ksum);
   psum = warp_sum_u64(psum);
@@ -363,7 +403,7 @@ static int launch_probe_w(const ProbeArgs &a, cudaStream_t st) {
     CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE, MODE, W32>, kPbThreads, 0));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
-  size_t ntiles = (a.n + kPbTile - 1) / kPbTile;
+  size_t ntiles = a.seg_parts ? (size_t) a.seg_parts * (size_t) (a.seg_cap / kPbTile) : (a.n + kPbTile - 1) / kPbTile;
   size_t grid = (size_t) sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid == 0) grid = 1;
@@ -398,6 +438,7 @@ static int dispatch_probe(int mode, const cc_ht *ht, const ProbeArgs &a, cudaStr
 static int g_strategy = 0;                // 0 auto, 1 direct, 2 partitioned
 static int g_mode_partitioned = 2;        // cache mode of the probe kernel behind the partition pass
 static int g_mode_direct = 0;             // cache mode of the direct probe
+static int g_single_pass = 1;             // partitioned strategy: single-pass partition with a device-side two-pass fallback
 static size_t g_slice_bytes = 32u << 20;  // target table bytes per partition (measured sweep: profiles/r1_sweep_slices.txt)
 
 // optional live phase timing (bench.py): CUDA events on the launching stream around the three kernels
@@ -441,6 +482,12 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
   a.cap = (d_out_key || d_out_payload || d_out_rowid) ? cap : 0;
   a.res = d_result;
   a.tile_counter = nullptr;
+  a.seg_prefix = nullptr;
+  a.seg_cursors = nullptr;
+  a.seg_cap = 0;
+  a.seg_parts = 0;
+  a.gate = nullptr;
+  a.gate_want = 0;
   CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
   if (n) {
     const bool part = want_partitioned(ht, n, d_out_rowid);
@@ -452,28 +499,64 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
     if (log2p > log2_slots) log2p = log2_slots;
     if (log2p < 1) log2p = 1;
     const int parts = part ? 1 << log2p : 0;
-    // stream-ordered scratch: [tile counter | 3 x parts partition control words] (+ the partitioned keys)
+    // stream-ordered scratch: control words [0] tile counter, [1] tile counter of the fallback probe, [2] overflow flag,
+    // [8 ..) cursors | counts | offsets (parts each) | tile prefix (parts + 1 uint32), plus the partitioned keys
     unsigned long long *ctl = nullptr;
     int64_t *scratch = nullptr;
-    CC_CUDA(cudaMallocAsync(&ctl, (8 + 3 * (size_t) parts) * sizeof(unsigned long long), st));
+    const size_t ctl_words = 8 + 4 * (size_t) parts + 8;
+    CC_CUDA(cudaMallocAsync(&ctl, ctl_words * sizeof(unsigned long long), st));
     CC_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
     a.tile_counter = ctl;
     int rc = CC_OK;
     if (part) {
-      cudaError_t e = cudaMallocAsync(&scratch, n * sizeof(int64_t), st);
+      // single-pass partition: fixed regions with 12.5 % slack, no histogram pass; skewed inputs overrun a region, raise
+      // the flag, and the gated two-pass sequence below redoes the work -- decided on the device, no host round trip
+      const bool single = g_single_pass != 0;
+      unsigned long long cap_rows = single ? ((n / parts) + (n / parts) / 8 + 2 * (size_t) kPartTile + kPbTile - 1) / kPbTile * kPbTile : 0;
+      const size_t scratch_rows = single ? (size_t) parts * cap_rows : n;
+      cudaError_t e = cudaMallocAsync(&scratch, scratch_rows * sizeof(int64_t), st);
       if (e != cudaSuccess) {
         cudaGetLastError();
         cudaFreeAsync(ctl, st);
-        set_error("partitioned probe: cannot allocate %zu bytes of scratch: %s", n * sizeof(int64_t), cudaGetErrorString(e));
+        set_error("partitioned probe: cannot allocate %zu bytes of scratch: %s", scratch_rows * sizeof(int64_t), cudaGetErrorString(e));
         return CC_ERR_NOMEM;
       }
+      const PartFn fn = PartFn::slot_bits(ht->mask, log2_slots, log2p);
+      unsigned long long *cursors = ctl + 8, *counts = ctl + 8 + parts, *offsets = ctl + 8 + 2 * parts;
+      uint32_t *prefix = reinterpret_cast<uint32_t *>(ctl + 8 + 3 * parts);
+      int *flag = reinterpret_cast<int *>(ctl + 2);
       profile_mark(0, st);
-      rc = partition_device(d_keys, n, PartFn::slot_bits(ht->mask, log2_slots, log2p), ctl + 8, ctl + 8 + parts, ctl + 8 + 2 * parts, scratch, st,
-                            g_profile ? &g_ev[1] : nullptr);
-      profile_mark(2, st);
-      if (rc == CC_OK) {
-        a.keys = scratch;
-        rc = dispatch_probe(g_mode_partitioned, ht, a, st);
+      if (single) {
+        if (g_profile) profile_mark(1, st);
+        rc = partition_single_device(d_keys, n, fn, cap_rows, cursors, flag, kPbTile, prefix, scratch, st);
+        profile_mark(2, st);
+        if (rc == CC_OK) {
+          ProbeArgs b = a;
+          b.keys = scratch;
+          b.seg_prefix = prefix;
+          b.seg_cursors = cursors;
+          b.seg_cap = cap_rows;
+          b.seg_parts = parts;
+          b.gate = flag;
+          b.gate_want = 0;
+          rc = dispatch_probe(g_mode_partitioned, ht, b, st);
+        }
+        if (rc == CC_OK) rc = partition_device(d_keys, n, fn, counts, offsets, cursors, scratch, st, nullptr, flag);  // gated fallback
+        if (rc == CC_OK) {
+          ProbeArgs b = a;
+          b.keys = scratch;
+          b.tile_counter = ctl + 1;
+          b.gate = flag;
+          b.gate_want = 1;
+          rc = dispatch_probe(g_mode_partitioned, ht, b, st);
+        }
+      } else {
+        rc = partition_device(d_keys, n, fn, counts, offsets, cursors, scratch, st, g_profile ? &g_ev[1] : nullptr);
+        profile_mark(2, st);
+        if (rc == CC_OK) {
+          a.keys = scratch;
+          rc = dispatch_probe(g_mode_partitioned, ht, a, st);
+        }
       }
       profile_mark(3, st);
       g_ev_valid = g_profile ? 2 : 0;
@@ -501,8 +584,9 @@ using namespace ccb;
 extern "C" {
 
 int cc_probe_set_strategy(int strategy, size_t slice_bytes) {
-  CC_REQUIRE(strategy >= 0 && strategy <= 2, "strategy must be 0 (auto), 1 (direct) or 2 (partitioned)");
-  g_strategy = strategy;
+  CC_REQUIRE(strategy >= 0 && strategy <= 3, "strategy must be 0 (auto), 1 (direct), 2 (partitioned) or 3 (partitioned, two-pass)");
+  g_single_pass = strategy != 3;
+  g_strategy = strategy == 3 ? 2 : strategy;
   if (slice_bytes) g_slice_bytes = slice_bytes;
   return CC_OK;
 }

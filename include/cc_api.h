@@ -193,7 +193,8 @@ int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_
 /* Probe strategy for tables far larger than L2 (process-wide):
  *   0 auto (default): partition the probe keys by table slice when the table is >= 96 MiB, the
  *     batch holds >= max(4 Mi, table_bytes / 64) keys (each 128-byte table line is revisited)
- *     and no row ids are requested; 1 always direct; 2 always partitioned.
+ *     and no row ids are requested; 1 always direct; 2 always partitioned; 3 always partitioned with the
+ *     two-pass (histogram + scatter) partition instead of the default single-pass one.
  * slice_bytes: target table bytes per partition (0 keeps the current value, default 16 MiB).
  * The partitioned path needs n * 8 bytes of stream-ordered scratch (cudaMallocAsync).       */
 int cc_probe_set_strategy(int strategy, size_t slice_bytes);

@@ -238,16 +238,16 @@ def test_facade_pipeline_matches_reference_tuples(ccb, name):
 
 
 # ------------------------------------------------------------------ batch probe (fast path)
-@pytest.fixture(params=["direct", "partitioned"])
+@pytest.fixture(params=["direct", "partitioned", "partitioned_two_pass"])
 def strategy(request, ccb):
-    """Both probe strategies: direct, and key partitioning by table slice (forced, with tiny 16 KiB slices
-    so that even the small test tables are split into many partitions)."""
+    """All probe strategies: direct, and key partitioning by table slice (forced, with tiny 16 KiB slices so that
+    even the small test tables are split into many partitions) with the single-pass and the two-pass partition."""
     if request.param == "direct":
         ccb.set_probe_strategy(1)
     else:
-        ccb.set_probe_strategy(2, 16 << 10)
+        ccb.set_probe_strategy(2 if request.param == "partitioned" else 3, 16 << 10)
     yield request.param
-    ccb.set_probe_strategy(0, 16 << 20)
+    ccb.set_probe_strategy(0, 32 << 20)
 
 
 @pytest.mark.parametrize("kind", [0, 1])
@@ -309,8 +309,8 @@ def test_probe_batch_large_properties(ccb, strategy):
     """Size-independent properties at a DRAM-resident size: hit=1 => every probe matches exactly once,
     key checksum == payload checksum == sum of inputs; hit=2 => matches are exactly the keys < n."""
     n = 1 << 24
-    if strategy == "partitioned":
-        ccb.set_probe_strategy(2, 8 << 20)
+    if strategy != "direct":
+        ccb.set_probe_strategy(2 if strategy == "partitioned" else 3, 8 << 20)
     for T in (ccb.LPHashTable, ccb.HashTable):
         tab = T(n, 1)
         assert tab.info().has_duplicates == 0
@@ -532,3 +532,27 @@ def test_partition_scatter_peers(ccb, log2p, n):
             assert np.all(got[: base[p]] == -7) and np.all(got[base[p] + counts[p]:] == -7)
             assert np.array_equal(np.sort(got[base[p]: base[p] + counts[p]]), np.sort(keys[pid == p])), (p, blocks)
     ccb._lib.check(ccb.lib().cc_partition_set_peer_blocks(0))
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_probe_batch_skewed_keys_take_the_fallback(ccb, kind):
+    """Single-pass partition regions have 12.5 % slack; heavily skewed probe keys overrun a region, which must
+    switch (on the device) to the two-pass partition with identical results."""
+    n = 200000
+    bk = O.build_keys(n, 2)
+    T, OT = (ccb.LPHashTable, O.OracleLP) if kind == 0 else (ccb.HashTable, O.OracleChain)
+    tab, otab = T(n, 2), OT(bk)
+    rng = np.random.Generator(np.random.PCG64(77))
+    for name, keys in {"all_equal_hit": np.full(300000, 1234, dtype=np.int64), "all_equal_miss": np.full(300000, 1235, dtype=np.int64),
+                       "half_one_key": np.where(rng.random(400000) < 0.5, 4242, rng.integers(0, 2 * n, size=400000)).astype(np.int64),
+                       "two_hot_keys": rng.choice(np.array([10, 199998], dtype=np.int64), size=250001)}.items():
+        want = O.pipeline([otab], keys.reshape(-1, 1), 2048)
+        try:
+            ccb.set_probe_strategy(2, 64 << 10)
+            r = tab.probe_batch(dev(keys), capacity=2 * keys.size + 8)
+        finally:
+            ccb.set_probe_strategy(0, 32 << 20)
+        assert (r["n_matches"], r["key_sum"], r["payload_sum"], r["overflow"]) == (want["n_tuples"], want["colsum"][0], want["colsum"][2], 0), name
+        m = r["n_matches"]
+        got = r["out_key"][:m].cpu().numpy()
+        assert np.array_equal(np.sort(got), np.sort(np.repeat(keys[np.isin(keys, bk)], 2)))

@@ -13,8 +13,9 @@ ok = torch.empty(npb, dtype=torch.int64, device="cuda")
 op = torch.empty(npb, dtype=torch.int64, device="cuda")
 res = torch.zeros(4, dtype=torch.int64, device="cuda")
 pkg.set_probe_profiling(True)
-for slice_mb in (8, 16, 32, 64, 128, 256):
-    pkg.set_probe_strategy(2, slice_mb << 20)
+import itertools
+for strat, slice_mb in itertools.product((2, 3), (32, 64)):
+    pkg.set_probe_strategy(strat, slice_mb << 20)
     best = None
     for _ in range(4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,4 +28,4 @@ for slice_mb in (8, 16, 32, 64, 128, 256):
         if best is None or t < best[0]:
             best = (t, ph)
     assert int(res[0].item()) == npb
-    print(f"slice {slice_mb:4d} MiB (P={max(2, (8 << 30) // (slice_mb << 20))}): total {best[0]:6.2f} ms  count {best[1][0]:5.2f}  scatter {best[1][1]:5.2f}  probe {best[1][2]:5.2f}", flush=True)
+    print(f"strategy {strat} ({'single-pass' if strat == 2 else 'two-pass'}) slice {slice_mb:4d} MiB (P={max(2, (8 << 30) // (slice_mb << 20))}): total {best[0]:6.2f} ms  count {best[1][0]:5.2f}  scatter {best[1][1]:5.2f}  probe {best[1][2]:5.2f}", flush=True)
