@@ -392,6 +392,236 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Lean kernel for tables WITHOUT duplicate keys and at most 2^32 slots / buckets (the C1 / C4 / C5 shape).  Same tiles, same
+// dynamic tile scheduling and the same compaction as probe_batch_kernel, restructured for instruction count -- the generic
+// kernel spends ~180 SASS instructions per key (ncu: 12.2 G warp instructions per 2^31 keys, issue slots the limiter):
+//   * 32-bit slot arithmetic throughout, one IMAD.WIDE per table address (forced with inline PTX: the optimiser otherwise
+//     rewrites zext(trunc(hash)) * 8 into 64-bit shift/mask sequences);
+//   * lane state in two bit masks (um = still walking, mm = matched), recomputed from the loaded slots after every lap --
+//     a resolved key keeps its last slot value, so the recomputation is idempotent and needs no per-key branches;
+//   * the walk past the home slot only loads for the keys that need it (~13 % at load factor 0.25);
+//   * the payload of a match is the matched build key == the probe key, so nothing but the key is kept after the compare
+//     and one checksum serves both result columns;
+//   * ranks come from one counter per WARP (8 instead of 32 shared-memory words), output pointers are formed once per
+//     tile, and the capacity check is one 32-bit compare per row;
+//   * all shared state is double-buffered by tile parity, which removes the third barrier per tile;
+//   * segmented key columns are walked with a forward-only cursor over the per-partition tile prefix (tile indices handed
+//     to a CTA only grow): no division, and no empty slack tiles that would cost an extra round trip to the tile counter.
+struct LeanShared {
+  uint32_t cnt[2][kPbWarps];
+  unsigned long long base[2];
+  unsigned long long off[2];
+  uint32_t rows[2];
+  // thread 0's cursor over the segmented key column
+  uint32_t seg_p, seg_lo, seg_hi, seg_total;
+  unsigned long long seg_cnt;
+};
+
+__device__ __forceinline__ const uint64_t *elem_ptr_u64(const void *base, uint32_t idx) {  // base + idx * 8 in ONE IMAD.WIDE.U32
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(r) : "r"(idx), "l"(base));
+  return reinterpret_cast<const uint64_t *>(r);
+}
+__device__ __forceinline__ uint32_t home_slot32(uint64_t key, uint32_t mask) {  // (uint32_t) murmurhash64(key) & mask
+  uint64_t x = key;
+  x ^= x >> 32;
+  x *= 0xd6e8feb86659fd93ULL;
+  x ^= x >> 32;
+  x *= 0xd6e8feb86659fd93ULL;
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+  return (lo ^ hi) & mask;
+}
+
+// thread 0: translate tile index g (dense numbering over the non-empty tiles) into (first row, row count); rows == 0: no tile left
+__device__ __forceinline__ void lean_tile(const ProbeArgs &a, LeanShared &sh, unsigned long long g, unsigned long long &off, uint32_t &rows) {
+  off = 0;
+  rows = 0;
+  if (a.seg_parts == 0) {
+    const unsigned long long ntiles = (a.n + kPbTile - 1) / kPbTile;
+    if (g >= ntiles) return;
+    off = g * (unsigned long long) kPbTile;
+    rows = (uint32_t) (a.n - off < (unsigned long long) kPbTile ? a.n - off : (unsigned long long) kPbTile);
+    return;
+  }
+  if (g >= sh.seg_total) return;
+  uint32_t p = sh.seg_p, lo = sh.seg_lo, hi = sh.seg_hi;
+  if ((uint32_t) g >= hi) {
+    do {
+      ++p;
+      lo = hi;
+      hi = __ldg(a.seg_prefix + p + 1);
+    } while ((uint32_t) g >= hi);
+    unsigned long long c = __ldg(a.seg_cursors + p);
+    sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
+    sh.seg_p = p;
+    sh.seg_lo = lo;
+    sh.seg_hi = hi;
+  }
+  const unsigned long long first = (unsigned long long) ((uint32_t) g - lo) * kPbTile;
+  const unsigned long long left = sh.seg_cnt - first;
+  off = (unsigned long long) p * a.seg_cap + first;
+  rows = left < (unsigned long long) kPbTile ? (uint32_t) left : (uint32_t) kPbTile;
+}
+
+template <int MODE>
+__device__ __forceinline__ void lean_load_keys(const ProbeArgs &a, const CachePolicy &pol, unsigned long long off, uint32_t rows,
+                                               uint64_t (&kn)[kPbKeysPerThread]) {
+  const int64_t *p = a.keys + off + threadIdx.x;
+  asm("" : "+l"(p));  // keep ONE base pointer; the four loads use immediate offsets
+#pragma unroll
+  for (int j = 0; j < kPbKeysPerThread; ++j)
+    kn[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_stream_u64<MODE>(p + j * kPbThreads, pol) : 0;
+}
+
+// OUT: which result columns exist, as a compile-time constant for the two hot shapes -- 0 = none (count + checksums only),
+// 3 = key + payload; -1 = decided at run time (row ids, single columns)
+template <int KIND, int MODE, int OUT>
+__global__ void __launch_bounds__(kPbThreads, 4) probe_unique_kernel(ProbeArgs a) {
+  __shared__ LeanShared sh;
+  const CachePolicy pol = make_policies();
+  if (a.gate && ((*a.gate != 0) != (a.gate_want != 0))) return;  // device-side strategy switch (CTA-uniform)
+  const uint32_t mask = (uint32_t) a.mask;
+  const unsigned lane = lane_id(), w = threadIdx.x >> 5, lt = lanemask_lt();
+  const unsigned outsel = OUT >= 0 ? (unsigned) OUT : ((a.out_key ? 1u : 0u) | (a.out_payload ? 2u : 0u) | (a.out_rowid ? 4u : 0u));
+  uint64_t ksum = 0;
+  if (threadIdx.x == 0) {
+    if (a.seg_parts) {
+      unsigned long long c = a.seg_cursors[0];
+      sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
+      sh.seg_p = 0;
+      sh.seg_lo = 0;
+      sh.seg_hi = a.seg_prefix[1];
+      sh.seg_total = a.seg_prefix[a.seg_parts];
+    }
+    lean_tile(a, sh, atomicAdd(a.tile_counter, 1ull), sh.off[0], sh.rows[0]);
+    lean_tile(a, sh, atomicAdd(a.tile_counter, 1ull), sh.off[1], sh.rows[1]);
+  }
+  __syncthreads();
+  unsigned long long off = sh.off[0], noff = sh.off[1];
+  uint32_t rows = sh.rows[0], nrows = sh.rows[1];
+  __syncthreads();
+  uint64_t kn[kPbKeysPerThread];
+  lean_load_keys<MODE>(a, pol, off, rows, kn);
+  unsigned par = 0;
+  while (rows > 0) {
+    // thread 0 asks for the tile after next now and publishes it before the first emit barrier
+    unsigned long long g_after = 0;
+    if (threadIdx.x == 0) g_after = atomicAdd(a.tile_counter, 1ull);
+    uint64_t k[kPbKeysPerThread], v[kPbKeysPerThread];
+    uint32_t p[kPbKeysPerThread], e[kPbKeysPerThread];
+    // ---- Probe (linear_probing_ht.cpp:45-57 / chaining_ht.cpp:44-55): all home-slot loads of a thread in flight together
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      k[j] = kn[j];
+      p[j] = home_slot32(k[j], mask);
+    }
+    if (KIND == CC_HT_LP) {
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j)
+        v[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_table_u64<MODE>(elem_ptr_u64(a.slots, p[j]), pol) : kEmptyU;
+      lean_load_keys<MODE>(a, pol, noff, nrows, kn);  // next tile's keys, behind this tile's gathers
+    } else {
+      uint2 d[kPbKeysPerThread];
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j)
+        d[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_table_u32x2<MODE>(reinterpret_cast<const uint2 *>(elem_ptr_u64(a.dir, p[j])), pol)
+                                                                : make_uint2(0u, 0u);
+      lean_load_keys<MODE>(a, pol, noff, nrows, kn);
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) {
+        p[j] = d[j].x;
+        e[j] = d[j].y ? d[j].x + d[j].y : d[j].x + 1u;  // empty bucket: looks like a one-entry chain whose entry never matches
+        v[j] = d[j].y ? ld_table_u64<MODE>(elem_ptr_u64(a.ckeys, p[j]), pol) : ~k[j];
+      }
+    }
+    // ---- walk (LPScanStructure::Next, linear_probing_ht.cpp:62-115 / AdvancePointers, chaining_ht.cpp:109-124) up to
+    // the first match: beyond it only duplicates could follow, and this table has none.  All unresolved keys of a thread
+    // advance together (one dependent load per lap).
+    unsigned um, mm;
+    for (;;) {
+      um = 0;
+      mm = 0;
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) {
+        const bool hit = v[j] == k[j];
+        const bool more = KIND == CC_HT_LP ? v[j] != kEmptyU : p[j] + 1u != e[j];
+        mm |= hit ? (1u << j) : 0u;
+        um |= (!hit && more) ? (1u << j) : 0u;
+      }
+      if (!um) break;
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) {
+        if (um & (1u << j)) {
+          p[j] = KIND == CC_HT_LP ? (p[j] + 1u) & mask : p[j] + 1u;
+          v[j] = ld_table_u64<MODE>(elem_ptr_u64(KIND == CC_HT_LP ? (const void *) a.slots : (const void *) a.ckeys, p[j]), pol);
+        }
+      }
+    }
+    // ---- compaction: per-warp match count -> scan over the 8 warps -> ONE atomicAdd -> coalesced stores
+    unsigned bal[kPbKeysPerThread];
+    uint32_t wtotal = 0;
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      bal[j] = __ballot_sync(0xffffffffu, (mm & (1u << j)) != 0u);
+      wtotal += __popc(bal[j]);
+    }
+    if (lane == 0) sh.cnt[par][w] = wtotal;
+    if (threadIdx.x == 0) lean_tile(a, sh, g_after, sh.off[par], sh.rows[par]);
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t c = lane < kPbWarps ? sh.cnt[par][lane] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < kPbWarps; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned) o) incl += t;
+      }
+      if (lane < kPbWarps) sh.cnt[par][lane] = incl - c;
+      if (lane == kPbWarps - 1) sh.base[par] = incl ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) incl) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long wbase = sh.base[par] + sh.cnt[par][w];  // first output row of this warp
+    // rows of this warp that still fit: everything in the common case, else what is left below the capacity
+    const uint32_t room = wbase + kPbTile <= a.cap ? 0xFFFFFFFFu : (a.cap > wbase ? (uint32_t) (a.cap - wbase) : 0u);
+    const int64_t *ok = a.out_key + wbase, *op = a.out_payload + wbase;
+    const uint64_t *orow = a.out_rowid + wbase;
+    asm("" : "+l"(ok));
+    asm("" : "+l"(op));
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      const uint32_t rel = run + __popc(bal[j] & lt);
+      run += __popc(bal[j]);
+      if (mm & (1u << j)) {
+        ksum += k[j];
+        if (OUT != 0 && rel < room) {
+          if (OUT == 3) {
+            st_stream_u64<MODE>((void *) elem_ptr_u64(ok, rel), k[j], pol);
+            st_stream_u64<MODE>((void *) elem_ptr_u64(op, rel), k[j], pol);
+          } else {
+            if (outsel & 1u) st_stream_u64<MODE>((void *) elem_ptr_u64(ok, rel), k[j], pol);
+            if (outsel & 2u) st_stream_u64<MODE>((void *) elem_ptr_u64(op, rel), k[j], pol);
+            if (outsel & 4u) st_stream_u64<MODE>((void *) elem_ptr_u64(orow, rel), off + (uint32_t) (j * kPbThreads) + threadIdx.x, pol);
+          }
+        }
+      }
+    }
+    // the tile published before the barriers of this iteration becomes the prefetched one
+    off = noff;
+    rows = nrows;
+    noff = sh.off[par];
+    nrows = sh.rows[par];
+    par ^= 1u;
+  }
+  ksum = warp_sum_u64(ksum);
+  if (lane == 0 && ksum) {
+    atomicAdd((unsigned long long *) &a.res->key_sum, (unsigned long long) ksum);
+    atomicAdd((unsigned long long *) &a.res->payload_sum, (unsigned long long) ksum);  // payload == matched build key == probe key
+  }
+}
+
 __global__ void probe_finish_kernel(cc_probe_result *res, size_t cap) {
   if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = res->n_matches > cap ? 1 : 0;
 }
@@ -412,8 +642,41 @@ static int launch_probe_w(const ProbeArgs &a, cudaStream_t st) {
   return CC_OK;
 }
 
+template <int KIND, int MODE, int OUT>
+static int launch_probe_lean_out(const ProbeArgs &a, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_unique_kernel<KIND, MODE, OUT>, kPbThreads, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  size_t ntiles = a.seg_parts ? (size_t) a.seg_parts * (size_t) (a.seg_cap / kPbTile) : (a.n + kPbTile - 1) / kPbTile;
+  size_t grid = (size_t) sm_count() * blocks_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid == 0) grid = 1;
+  probe_unique_kernel<KIND, MODE, OUT><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+template <int KIND, int MODE>
+static int launch_probe_lean(const ProbeArgs &a, cudaStream_t st) {
+  if (a.out_key && a.out_payload && !a.out_rowid) return launch_probe_lean_out<KIND, MODE, 3>(a, st);
+  if (!a.out_key && !a.out_payload && !a.out_rowid) return launch_probe_lean_out<KIND, MODE, 0>(a, st);
+  return launch_probe_lean_out<KIND, MODE, -1>(a, st);
+}
+
+// A/B switch for measurements: CCB_PROBE_GENERIC=1 in the environment routes every probe through the generic kernel
+static bool lean_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("CCB_PROBE_GENERIC");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 template <int KIND, bool UNIQUE, int MODE>
 static int launch_probe(const ProbeArgs &a, cudaStream_t st) {
+  if (UNIQUE && lean_enabled() && a.mask <= 0xFFFFFFFFull) return launch_probe_lean<KIND, MODE>(a, st);
   return a.mask <= 0xFFFFFFFFull ? launch_probe_w<KIND, UNIQUE, MODE, true>(a, st) : launch_probe_w<KIND, UNIQUE, MODE, false>(a, st);
 }
 
