@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libccb200.so")
+LIB_PATH = os.environ.get("CCB_LIB_PATH") or os.path.join(PKG_DIR, "libccb200.so")  # override: A/B builds of the same ABI
 
 CC_HT_LP = 0
 CC_HT_CHAIN = 1

@@ -73,6 +73,10 @@ __global__ void partition_offsets_kernel(const unsigned long long *__restrict__ 
 // PEERS == true : partition p is written into dst.p[p] -- a buffer that may be PEER memory of another
 //                 GPU (CUDA IPC mapping over NVLink): the scatter IS the exchange, row runs travel as
 //                 coalesced stores straight into the owner's receive buffer.
+// s_delta marker of a run that overran its region.  A valid delta is (global row) - (offset in the tile), i.e. anything in
+// [-kPartTile, 2^62): -1 is a legitimate value (it used to be the marker, which silently dropped such a run), 2^63 is not.
+constexpr unsigned long long kDroppedRun = 1ull << 63;
+
 struct ScatterDst {
   int64_t *p[kMaxPeers];
 };
@@ -200,14 +204,14 @@ __global__ void __launch_bounds__(kPartThreads)
 #pragma unroll
     for (int q = 0; q < kBins; ++q) {
       int i = threadIdx.x * kBins + q;
-      if (i < parts) s_delta[i] = gbase[q] == ~0ull ? ~0ull : gbase[q] - first[q];
+      if (i < parts) s_delta[i] = gbase[q] == ~0ull ? kDroppedRun : gbase[q] - first[q];
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
       uint32_t pp = s_part[i];
       int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
       unsigned long long d = s_delta[pp];
-      if (d != ~0ull) out[d + i] = (int64_t) s_sorted[i];
+      if (d != kDroppedRun) out[d + i] = (int64_t) s_sorted[i];
     }
     __syncthreads();
   }

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
 //   * all shared state is double-buffered by tile parity, which removes the third barrier per tile;
 //   * segmented key columns are walked with a forward-only cursor over the per-partition tile prefix (tile indices handed
 //     to a CTA only grow): no division, and no empty slack tiles that would cost an extra round trip to the tile counter.
-struct LeanShared {
+struct __align__(16) LeanShared {
   uint32_t cnt[2][kPbWarps];
   unsigned long long base[2];
   unsigned long long off[2];
@@ -416,6 +416,11 @@ struct LeanShared {
   // thread 0's cursor over the segmented key column
   uint32_t seg_p, seg_lo, seg_hi, seg_total;
   unsigned long long seg_cnt;
+  // LP tables: per-warp queue of the keys whose home slot holds another key (~13 % at load factor 0.25); after the
+  // tail walk its first entries are the tail's matches
+  uint64_t queue[kPbWarps][kPbKeysPerThread * 32];
+  // per-warp parking area of the matches of one tile (at most 128 keys), flushed to the output one iteration later
+  uint64_t stage[kPbWarps][kPbKeysPerThread * 32];
 };
 
 __device__ __forceinline__ const uint64_t *elem_ptr_u64(const void *base, uint32_t idx) {  // base + idx * 8 in ONE IMAD.WIDE.U32
@@ -432,6 +437,17 @@ __device__ __forceinline__ uint32_t home_slot32(uint64_t key, uint32_t mask) {  
   uint32_t lo, hi;
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
   return (lo ^ hi) & mask;
+}
+
+// one aligned 32-byte sector (4 table slots, slot index s % 4 == 0) in ONE request: the load/store unit hands one request per
+// lane and cycle to the memory system whatever its width, and that request rate is what bounds this kernel
+template <int MODE>
+__device__ __forceinline__ void ld_table_sector(const uint64_t *slots, uint32_t s, const CachePolicy &pol, uint64_t (&x)[4]) {
+  const uint64_t *pa = elem_ptr_u64(slots, s);
+  if (MODE & 2)
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(pa), "l"(pol.last));
+  else
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(pa));
 }
 
 // thread 0: translate tile index g (dense numbering over the non-empty tiles) into (first row, row count); rows == 0: no tile left
@@ -465,6 +481,24 @@ __device__ __forceinline__ void lean_tile(const ProbeArgs &a, LeanShared &sh, un
   rows = left < (unsigned long long) kPbTile ? (uint32_t) left : (uint32_t) kPbTile;
 }
 
+// write the `cnt` rows a warp parked in shared memory to output rows [first, first + cnt): lane l stores rows l, l + 32, ...
+template <int MODE, int OUT>
+__device__ __forceinline__ void lean_flush(const ProbeArgs &a, const CachePolicy &pol, const uint64_t *stage, unsigned long long first,
+                                           uint32_t cnt, unsigned outsel, unsigned lane) {
+  if (OUT == 0) return;
+  // rows of this warp that still fit: everything in the common case, else what is left below the capacity
+  const uint32_t room = first + kPbTile <= a.cap ? 0xFFFFFFFFu : (a.cap > first ? (uint32_t) (a.cap - first) : 0u);
+  const uint32_t n = cnt < room ? cnt : room;
+  const int64_t *ok = a.out_key + first, *op = a.out_payload + first;
+  asm("" : "+l"(ok));
+  asm("" : "+l"(op));
+  for (uint32_t r = lane; r < n; r += 32) {
+    const uint64_t key = stage[r];
+    if (OUT == 3 || (outsel & 1u)) st_stream_u64<MODE>((void *) elem_ptr_u64(ok, r), key, pol);
+    if (OUT == 3 || (outsel & 2u)) st_stream_u64<MODE>((void *) elem_ptr_u64(op, r), key, pol);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void lean_load_keys(const ProbeArgs &a, const CachePolicy &pol, unsigned long long off, uint32_t rows,
                                                uint64_t (&kn)[kPbKeysPerThread]) {
@@ -477,8 +511,11 @@ __device__ __forceinline__ void lean_load_keys(const ProbeArgs &a, const CachePo
 
 // OUT: which result columns exist, as a compile-time constant for the two hot shapes -- 0 = none (count + checksums only),
 // 3 = key + payload; -1 = decided at run time (row ids, single columns)
+#ifndef CCB_LEAN_MIN_BLOCKS
+#define CCB_LEAN_MIN_BLOCKS 4
+#endif
 template <int KIND, int MODE, int OUT>
-__global__ void __launch_bounds__(kPbThreads, 4) probe_unique_kernel(ProbeArgs a) {
+__global__ void __launch_bounds__(kPbThreads, CCB_LEAN_MIN_BLOCKS) probe_unique_kernel(ProbeArgs a) {
   __shared__ LeanShared sh;
   const CachePolicy pol = make_policies();
   if (a.gate && ((*a.gate != 0) != (a.gate_want != 0))) return;  // device-side strategy switch (CTA-uniform)
@@ -505,8 +542,10 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_unique_kernel(ProbeArgs a
   uint64_t kn[kPbKeysPerThread];
   lean_load_keys<MODE>(a, pol, off, rows, kn);
   unsigned par = 0;
+  uint32_t prev_woff = 0, prev_cnt = 0;   // this warp's share of the previous tile's output range
+  unsigned long long pending = 0;         // thread 0: output base of the previous tile (result of its atomicAdd)
   while (rows > 0) {
-    // thread 0 asks for the tile after next now and publishes it before the first emit barrier
+    // thread 0 asks for the tile after next now and publishes it before the emit barrier
     unsigned long long g_after = 0;
     if (threadIdx.x == 0) g_after = atomicAdd(a.tile_counter, 1ull);
     uint64_t k[kPbKeysPerThread], v[kPbKeysPerThread];
@@ -537,29 +576,85 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_unique_kernel(ProbeArgs a
       }
     }
     // ---- walk (LPScanStructure::Next, linear_probing_ht.cpp:62-115 / AdvancePointers, chaining_ht.cpp:109-124) up to
-    // the first match: beyond it only duplicates could follow, and this table has none.  All unresolved keys of a thread
-    // advance together (one dependent load per lap).
+    // the first match: beyond it only duplicates could follow, and this table has none.
     unsigned um, mm;
-    for (;;) {
+    uint32_t ntail = 0;  // LP: matches found by the tail walk, parked in sh.queue[w][0 .. ntail)
+    if (KIND == CC_HT_LP) {
+      // The CTA waits at the emit barrier for its SLOWEST key, and among 1024 keys the longest probe sequence is ~7 slots:
+      // walking them slot by slot costs ~7 dependent L2 round trips per tile.  Instead the unresolved keys of the warp are
+      // queued densely, one lane takes one key and examines a whole sector (4 slots, one request) per round trip.
       um = 0;
       mm = 0;
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
         const bool hit = v[j] == k[j];
-        const bool more = KIND == CC_HT_LP ? v[j] != kEmptyU : p[j] + 1u != e[j];
         mm |= hit ? (1u << j) : 0u;
-        um |= (!hit && more) ? (1u << j) : 0u;
+        um |= (!hit && v[j] != kEmptyU) ? (1u << j) : 0u;
       }
-      if (!um) break;
+      uint64_t *const q = sh.queue[w];
+      uint32_t nq = 0;
 #pragma unroll
       for (int j = 0; j < kPbKeysPerThread; ++j) {
-        if (um & (1u << j)) {
-          p[j] = KIND == CC_HT_LP ? (p[j] + 1u) & mask : p[j] + 1u;
-          v[j] = ld_table_u64<MODE>(elem_ptr_u64(KIND == CC_HT_LP ? (const void *) a.slots : (const void *) a.ckeys, p[j]), pol);
+        const unsigned bu = __ballot_sync(0xffffffffu, (um & (1u << j)) != 0u);
+        if (um & (1u << j)) q[nq + __popc(bu & lt)] = k[j];
+        nq += __popc(bu);
+      }
+      __syncwarp();
+      for (uint32_t b = 0; b < nq; b += 32) {
+        const bool act = b + lane < nq;
+        const uint64_t key = act ? q[b + lane] : 0;
+        uint32_t at = (home_slot32(key, mask) + 1u) & mask;  // the home slot itself holds another key
+        bool matched = false, open = act;
+        while (open) {
+          const uint32_t s0 = at & ~3u;
+          uint64_t x[4];
+          ld_table_sector<MODE>(a.slots, s0, pol, x);
+          unsigned eq = 0, stop = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            eq |= x[i] == key ? (1u << i) : 0u;
+            stop |= (x[i] == key || x[i] == kEmptyU) ? (1u << i) : 0u;
+          }
+          stop &= 0xFu << (at & 3u);  // slots before `at` were examined earlier
+          if (stop) {
+            matched = (eq & stop & (0u - stop)) != 0u;  // the first slot that ends the walk: the key, or an empty slot
+            open = false;
+          } else {
+            at = (s0 + 4u) & mask;
+          }
+        }
+        __syncwarp();  // every lane has read its queue entry before the match list overwrites the front of the queue
+        const unsigned bm = __ballot_sync(0xffffffffu, matched);
+        if (matched) q[ntail + __popc(bm & lt)] = key;
+        ntail += __popc(bm);
+      }
+      __syncwarp();
+    } else {
+      // chains of a duplicate-free table are short: all unresolved keys of a thread advance together, one entry per lap
+      for (;;) {
+        um = 0;
+        mm = 0;
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) {
+          const bool hit = v[j] == k[j];
+          mm |= hit ? (1u << j) : 0u;
+          um |= (!hit && p[j] + 1u != e[j]) ? (1u << j) : 0u;
+        }
+        if (!um) break;
+#pragma unroll
+        for (int j = 0; j < kPbKeysPerThread; ++j) {
+          if (um & (1u << j)) {
+            p[j] += 1u;
+            v[j] = ld_table_u64<MODE>(elem_ptr_u64(a.ckeys, p[j]), pol);
+          }
         }
       }
     }
-    // ---- compaction: per-warp match count -> scan over the 8 warps -> ONE atomicAdd -> coalesced stores
+    // ---- compaction, decoupled from the global round trip.  The warp PARKS its matches densely in its own region of
+    // shared memory and thread 0 issues the ONE atomicAdd that reserves the tile's output range; nobody waits for it.
+    // The parked rows are flushed one iteration later, when the reservation has long returned, with fully coalesced
+    // stores (a warp store covers 32 consecutive output rows).  One barrier per tile: every warp derives its own offset
+    // from the 8 published warp counts instead of waiting for a scan by warp 0.
     unsigned bal[kPbKeysPerThread];
     uint32_t wtotal = 0;
 #pragma unroll
@@ -567,54 +662,63 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_unique_kernel(ProbeArgs a
       bal[j] = __ballot_sync(0xffffffffu, (mm & (1u << j)) != 0u);
       wtotal += __popc(bal[j]);
     }
+    wtotal += ntail;
     if (lane == 0) sh.cnt[par][w] = wtotal;
-    if (threadIdx.x == 0) lean_tile(a, sh, g_after, sh.off[par], sh.rows[par]);
-    __syncthreads();
-    if (w == 0) {
-      const uint32_t c = lane < kPbWarps ? sh.cnt[par][lane] : 0u;
-      uint32_t incl = c;
-#pragma unroll
-      for (int o = 1; o < kPbWarps; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned) o) incl += t;
-      }
-      if (lane < kPbWarps) sh.cnt[par][lane] = incl - c;
-      if (lane == kPbWarps - 1) sh.base[par] = incl ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) incl) : 0ull;
+    if (threadIdx.x == 0) {
+      lean_tile(a, sh, g_after, sh.off[par], sh.rows[par]);
+      sh.base[par] = pending;  // output base of the PREVIOUS tile (reserved one iteration ago)
     }
     __syncthreads();
-    const unsigned long long wbase = sh.base[par] + sh.cnt[par][w];  // first output row of this warp
-    // rows of this warp that still fit: everything in the common case, else what is left below the capacity
-    const uint32_t room = wbase + kPbTile <= a.cap ? 0xFFFFFFFFu : (a.cap > wbase ? (uint32_t) (a.cap - wbase) : 0u);
-    const int64_t *ok = a.out_key + wbase, *op = a.out_payload + wbase;
-    const uint64_t *orow = a.out_rowid + wbase;
-    asm("" : "+l"(ok));
-    asm("" : "+l"(op));
-    uint32_t run = 0;
+    uint32_t woff = 0, total = 0;
+    {
+      const uint4 c0 = *reinterpret_cast<const uint4 *>(&sh.cnt[par][0]), c1 = *reinterpret_cast<const uint4 *>(&sh.cnt[par][4]);
+      const uint32_t c[kPbWarps] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-    for (int j = 0; j < kPbKeysPerThread; ++j) {
-      const uint32_t rel = run + __popc(bal[j] & lt);
-      run += __popc(bal[j]);
-      if (mm & (1u << j)) {
-        ksum += k[j];
-        if (OUT != 0 && rel < room) {
-          if (OUT == 3) {
-            st_stream_u64<MODE>((void *) elem_ptr_u64(ok, rel), k[j], pol);
-            st_stream_u64<MODE>((void *) elem_ptr_u64(op, rel), k[j], pol);
-          } else {
-            if (outsel & 1u) st_stream_u64<MODE>((void *) elem_ptr_u64(ok, rel), k[j], pol);
-            if (outsel & 2u) st_stream_u64<MODE>((void *) elem_ptr_u64(op, rel), k[j], pol);
-            if (outsel & 4u) st_stream_u64<MODE>((void *) elem_ptr_u64(orow, rel), off + (uint32_t) (j * kPbThreads) + threadIdx.x, pol);
-          }
+      for (int i = 0; i < kPbWarps; ++i) {
+        woff += (unsigned) i < w ? c[i] : 0u;
+        total += c[i];
+      }
+    }
+    lean_flush<MODE, OUT>(a, pol, sh.stage[w], sh.base[par] + prev_woff, prev_cnt, outsel, lane);
+    __syncwarp();
+    if (OUT != 0) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) {
+        if (mm & (1u << j)) {
+          ksum += k[j];
+          sh.stage[w][run + __popc(bal[j] & lt)] = k[j];
+        }
+        run += __popc(bal[j]);
+      }
+      if (KIND == CC_HT_LP) {
+        for (uint32_t i = lane; i < ntail; i += 32) {
+          const uint64_t key = sh.queue[w][i];
+          ksum += key;
+          sh.stage[w][run + i] = key;
         }
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) ksum += (mm & (1u << j)) ? k[j] : 0ull;
+      if (KIND == CC_HT_LP)
+        for (uint32_t i = lane; i < ntail; i += 32) ksum += sh.queue[w][i];
     }
-    // the tile published before the barriers of this iteration becomes the prefetched one
+    __syncwarp();  // parked rows are visible to the flushing lanes; the queue may be refilled
+    if (threadIdx.x == 0) pending = total ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) total) : 0ull;
+    prev_woff = woff;
+    prev_cnt = wtotal;
+    // the tile published before the barrier of this iteration becomes the prefetched one
     off = noff;
     rows = nrows;
     noff = sh.off[par];
     nrows = sh.rows[par];
     par ^= 1u;
   }
+  // flush the rows parked by the last iteration
+  if (threadIdx.x == 0) sh.base[par] = pending;
+  __syncthreads();
+  lean_flush<MODE, OUT>(a, pol, sh.stage[w], sh.base[par] + prev_woff, prev_cnt, outsel, lane);
   ksum = warp_sum_u64(ksum);
   if (lane == 0 && ksum) {
     atomicAdd((unsigned long long *) &a.res->key_sum, (unsigned long long) ksum);
@@ -653,7 +757,11 @@ static int launch_probe_lean_out(const ProbeArgs &a, cudaStream_t st) {
   size_t grid = (size_t) sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid == 0) grid = 1;
-  probe_unique_kernel<KIND, MODE, OUT><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
+  static const size_t extra_smem = [] {  // experiment knob: unused dynamic shared memory (L1 carve-out sensitivity)
+    const char *e = getenv("CCB_PROBE_EXTRA_SMEM");
+    return e ? (size_t) atoi(e) : (size_t) 0;
+  }();
+  probe_unique_kernel<KIND, MODE, OUT><<<(unsigned) grid, kPbThreads, extra_smem, st>>>(a);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -676,7 +784,7 @@ static bool lean_enabled() {
 
 template <int KIND, bool UNIQUE, int MODE>
 static int launch_probe(const ProbeArgs &a, cudaStream_t st) {
-  if (UNIQUE && lean_enabled() && a.mask <= 0xFFFFFFFFull) return launch_probe_lean<KIND, MODE>(a, st);
+  if (UNIQUE && lean_enabled() && a.mask <= 0xFFFFFFFFull && !a.out_rowid) return launch_probe_lean<KIND, MODE>(a, st);
   return a.mask <= 0xFFFFFFFFull ? launch_probe_w<KIND, UNIQUE, MODE, true>(a, st) : launch_probe_w<KIND, UNIQUE, MODE, false>(a, st);
 }
 
