@@ -168,15 +168,20 @@ def run_reference_arm(args):
     return 0
 
 
+EXCHANGES = {"ce": "probe side: single-pass owner partition + copy-engine block copies over NVLink underneath the probe of the previous sub-batch",
+             "p2p": "scatter kernel stores into peer memory over NVLink", "nccl": "NCCL all-to-all"}
+
+
 def workload_config(args) -> dict:
     if args.gpus == 1:
         return {"workload": f"C4: LP hash join, 2^{args.log2_build} build keys (cf=1, {8 * 4 << args.log2_build >> 30} GiB table), "
                             f"2^{args.log2_probe} probe keys/step (counter generator seed 2, hit=1), dense key+payload output",
                 "table": "linear_probing", "chunk": 1024, "l2_policy": "inputs (16 GiB keys, 8 GiB table) far exceed the 126 MB L2; no flush needed"}
     return {"workload": f"C5 share: hash-partitioned LP join, per GPU 2^{args.log2_build} build keys and 2^{args.log2_probe} probe keys/step, "
-                        f"exchange of both sides ({'scatter kernel stores into peer memory over NVLink' if args.exchange == 'p2p' else 'NCCL all-to-all'}), "
+                        f"exchange of both sides ({EXCHANGES[args.exchange]}), "
                         f"dense key+payload output (results stay sharded)",
-            "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "exchange": args.exchange, "l2_policy": "inputs far exceed L2; no flush needed"}
+            "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "exchange": args.exchange, "sub_batches": args.sub_batches,
+            "l2_policy": "inputs far exceed L2; no flush needed"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -193,9 +198,11 @@ def main() -> int:
     ap.add_argument("--cpu-log2-probe", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sub-batches", type=int, default=1, help="N>1 with p2p: shuffle of sub-batch b+1 overlaps the probe of sub-batch b")
+    ap.add_argument("--sub-batches", type=int, default=None,
+                    help="N>1: the exchange of sub-batch b+1 overlaps the probe of sub-batch b (default 4 with --exchange ce, else 1)")
     ap.add_argument("--peer-blocks", type=int, default=0, help="N>1 with p2p: CTA cap of the NVLink-bound peer scatter (0 = all SMs)")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory scatter or NCCL all-to-all")
+    ap.add_argument("--exchange", default="ce", choices=["ce", "p2p", "nccl"],
+                    help="N>1: copy-engine block copies under the probe (default), fused peer-memory scatter kernel, or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
@@ -203,6 +210,8 @@ def main() -> int:
         args.log2_build = 28 if args.gpus == 1 else 27
     if args.log2_probe is None:
         args.log2_probe = 31 if args.gpus == 1 else 30
+    if args.sub_batches is None:
+        args.sub_batches = 4 if (args.gpus > 1 and args.exchange == "ce") else 1
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -236,8 +245,9 @@ def main() -> int:
         par = importlib.import_module(PKG_NAME + ".parallel")
         key_space = n_build * world
         local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
+        cap_rows = -(-n_probe // args.sub_batches) if args.exchange == "ce" else int(n_probe * 1.05) + (1 << 20)
         join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
-                                   capacity_rows=int(n_probe * 1.05) + (1 << 20), peer_blocks=args.peer_blocks)
+                                   capacity_rows=cap_rows, peer_blocks=args.peer_blocks)
         table = join.table
         del local_build
     torch.cuda.synchronize()
@@ -250,7 +260,7 @@ def main() -> int:
     cap -= cap % max(1, args.sub_batches)
     out_key = torch.empty(cap, dtype=torch.int64, device=dev)
     out_payload = torch.empty(cap, dtype=torch.int64, device=dev)
-    n_sub = args.sub_batches if (distributed and args.exchange == "p2p") else 1
+    n_sub = args.sub_batches if (distributed and args.exchange in ("p2p", "ce")) else 1
     result = torch.zeros((n_sub, 4), dtype=torch.int64, device=dev)
     recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if (distributed and args.exchange == "nccl") else None
     expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
@@ -258,7 +268,7 @@ def main() -> int:
     def step():
         if not distributed:
             return table.probe_batch(keys, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
-        if args.exchange == "p2p":
+        if args.exchange in ("p2p", "ce"):
             return join.probe_pipelined(keys, n_sub, out_key, out_payload, result)
         shuffled = join.shuffle(keys, out=recv_buf)
         return table.probe_batch(shuffled, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
@@ -308,6 +318,8 @@ def main() -> int:
         t = torch.tensor([expected_sum - (1 << 64) if expected_sum >= (1 << 63) else expected_sum], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         expected_sum = int(t.item()) & ((1 << 64) - 1)
+    if distributed and join.copier is not None:
+        join.copier.check_overflow()
     assert overflow == 0, "output capacity overflow"
     assert n_matches == n_probe * world, (n_matches, n_probe * world)
     assert key_sum == expected_sum and payload_sum == expected_sum, "checksum mismatch"
@@ -321,7 +333,7 @@ def main() -> int:
             "checks": {"n_matches": n_matches, "key_sum_ok": True}}
 
     if rank == 0 or not distributed:
-        # roofline of the dominant kernel (probe_batch_kernel): algorithmic bytes per launch / event time
+        # roofline of the dominant kernel (probe_unique_kernel): algorithmic bytes per launch / event time
         if not distributed:
             kernel_ms = statistics.mean(step_ms)
             achieved = ALGO_BYTES_PER_TUPLE * n_probe / (kernel_ms * 1e-3) / 1e9
@@ -330,7 +342,7 @@ def main() -> int:
             kernels = [  # live CUDA-event time of every kernel of the step with its own algorithmic bytes
                 {"kernel": "partition_count_kernel", "ms": ph[0], "algorithmic_bytes": 8 * n_probe},
                 {"kernel": "partition_scatter_kernel", "ms": ph[1], "algorithmic_bytes": 16 * n_probe},
-                {"kernel": "probe_batch_kernel<LP,unique,hints,w32> (+ the gated no-op launches of the two-pass fallback)", "ms": ph[2],
+                {"kernel": "probe_unique_kernel<LP,hints,key+payload> (+ the gated no-op launches of the two-pass fallback)", "ms": ph[2],
                  "algorithmic_bytes": 24 * n_probe + tb},
             ]
             if ph[0] < 0.01:  # single-pass partition: there is no histogram pass
@@ -339,7 +351,7 @@ def main() -> int:
                 k["achieved_GBps"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
                 k["frac"] = k["achieved_GBps"] / peak if k["achieved_GBps"] else None
             line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                "traffic": load_traffic(), "kernel": "whole step = partition_scatter_kernel + probe_batch_kernel (dominant)",
+                                "traffic": load_traffic(), "kernel": "whole step = partition_scatter_kernel + probe_unique_kernel (dominant)",
                                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_tuple": ALGO_BYTES_PER_TUPLE, "peak_source": peak_src,
                                 "note": "achieved = 59 B x probe tuples / step time (SURVEY 8d C4 model, assumes one 32 B table sector per probe); "
                                         "the partitioned strategy streams the table once instead, see kernels[] for per-kernel figures",

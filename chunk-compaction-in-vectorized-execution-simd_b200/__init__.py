@@ -336,6 +336,23 @@ class _TableBase:
             out.update(n_matches=int(r[0]), key_sum=int(r[1]), payload_sum=int(r[2]), overflow=int(r[3]))
         return out
 
+    def probe_batch_segmented(self, keys: torch.Tensor, n_segments: int, segment_capacity: int, segment_counts: torch.Tensor, *,
+                              capacity: int, out_key: Optional[torch.Tensor] = None, out_payload: Optional[torch.Tensor] = None,
+                              result: Optional[torch.Tensor] = None, sync: bool = True) -> dict:
+        """cc_probe_batch_segmented: probe a segmented key column (segment s = keys[s * cap : s * cap + counts[s]], the counts
+        stay on the device).  `keys` must span n_segments * segment_capacity rows."""
+        assert keys.numel() >= n_segments * segment_capacity and segment_counts.dtype == torch.int64
+        if result is None:
+            result = torch.zeros(4, dtype=torch.int64, device="cuda")
+        L.check(lib().cc_probe_batch_segmented(self._h, _ptr(keys), n_segments, segment_capacity, _ptr(segment_counts), _ptr(out_key),
+                                               _ptr(out_payload), capacity if (out_key is not None or out_payload is not None) else 0,
+                                               _ptr(result), _stream()))
+        out = {"result_tensor": result, "out_key": out_key, "out_payload": out_payload}
+        if sync:
+            r = result.cpu().numpy().view(np.uint64)
+            out.update(n_matches=int(r[0]), key_sum=int(r[1]), payload_sum=int(r[2]), overflow=int(r[3]))
+        return out
+
     def probe_batch_host(self, h_keys: np.ndarray, h_out_key: Optional[np.ndarray], h_out_payload: Optional[np.ndarray]) -> dict:
         """End-to-end probe with HOST buffers (cc_probe_batch_host): H2D + probe + D2H inside."""
         r = ProbeResult()
@@ -560,6 +577,23 @@ def _chain_result_dict(r: ChainResult, J: int) -> dict:
 
 
 # ---- multi-GPU partitioning -----------------------------------------------------------------
+def partition_single(keys: torch.Tensor, log2_parts: int, region_capacity: int, out: Optional[torch.Tensor] = None,
+                     counts: Optional[torch.Tensor] = None, overflow: Optional[torch.Tensor] = None):
+    """cc_partition_single: single-pass hash partition into fixed regions of `region_capacity` rows.
+    Returns (out[P * region_capacity], counts[P] int64 device, overflow int32[1] device); nothing is synchronised."""
+    _ensure()
+    P = 1 << log2_parts
+    n = keys.numel()
+    if out is None:
+        out = torch.empty(P * region_capacity, dtype=torch.int64, device="cuda")
+    if counts is None:
+        counts = torch.zeros(P, dtype=torch.int64, device="cuda")
+    if overflow is None:
+        overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(lib().cc_partition_single(_ptr(keys) if n else None, n, log2_parts, region_capacity, _ptr(counts), _ptr(overflow), _ptr(out), _stream()))
+    return out, counts, overflow
+
+
 def partition_keys(keys: torch.Tensor, log2_parts: int):
     """Hash-partition a key column into 2^log2_parts contiguous segments.
     Returns (partitioned keys, counts[P] as a host numpy array, offsets[P])."""

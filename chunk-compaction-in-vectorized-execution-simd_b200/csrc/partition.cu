@@ -23,8 +23,21 @@
 namespace ccb {
 
 // gate (optional): the kernel only runs when *gate != 0 (device-side fallback switch, see partition_single_device)
+// rows of tile `tile` (kPartTile rows starting at row tile * kPartTile) that hold keys: plain column -> all but the ragged end;
+// segmented column -> what the tile's segment has filled there (0 for tiles in a segment's slack)
+__device__ __forceinline__ uint32_t tile_rows(size_t tile, size_t n, const SegIn &seg) {
+  const size_t tbase = tile * (size_t) kPartTile;
+  if (!seg.cap) return (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);
+  const uint32_t per_seg = (uint32_t) (seg.cap / kPartTile);
+  const uint32_t s = (uint32_t) tile / per_seg;
+  const unsigned long long first = (unsigned long long) ((uint32_t) tile - s * per_seg) * kPartTile;
+  unsigned long long c = __ldg(seg.counts + s);
+  if (c > seg.cap) c = seg.cap;
+  return c > first ? (uint32_t) (c - first < (unsigned long long) kPartTile ? c - first : (unsigned long long) kPartTile) : 0u;
+}
+
 __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn,
-                                                                       unsigned long long *counts, const int *gate) {
+                                                                       unsigned long long *counts, const int *gate, SegIn seg) {
   __shared__ uint32_t s_cnt[kMaxParts];
   if (gate && *gate == 0) return;
   const int parts = (int) fn.pmask + 1;
@@ -33,7 +46,7 @@ __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t tbase = tile * (size_t) kPartTile;
-    const uint32_t rows = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);  // CTA-uniform
+    const uint32_t rows = tile_rows(tile, n, seg);  // CTA-uniform
     const int64_t *src = keys + tbase + threadIdx.x;
     uint64_t k[kPartItems];
 #pragma unroll
@@ -49,7 +62,7 @@ __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int
 
 // exclusive scan of the P counters (single CTA), also resets the cursors
 __global__ void partition_offsets_kernel(const unsigned long long *__restrict__ counts, int parts, unsigned long long *offsets,
-                                         unsigned long long *cursors, const int *gate) {
+                                         unsigned long long *cursors, const int *gate, unsigned long long *total) {
   __shared__ unsigned long long s[kMaxParts];
   if (gate && *gate == 0) return;
   for (int i = threadIdx.x; i < parts; i += blockDim.x) s[i] = counts[i];
@@ -61,6 +74,7 @@ __global__ void partition_offsets_kernel(const unsigned long long *__restrict__ 
       s[i] = run;
       run += c;
     }
+    if (total) *total = run;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < parts; i += blockDim.x) {
@@ -87,7 +101,7 @@ struct ScatterDst {
 template <bool PEERS, bool TMA>
 __global__ void __launch_bounds__(kPartThreads)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
-                             unsigned long long *cursors, ScatterDst dst, unsigned long long cap_rows, int *flag, int gated) {
+                             unsigned long long *cursors, ScatterDst dst, unsigned long long cap_rows, int *flag, int gated, SegIn seg) {
   // cap_rows > 0 (single-pass mode): partition p owns the fixed region [p * cap_rows, (p + 1) * cap_rows) of the output, no
   //   histogram pass needed; a tile that would overrun a region raises *flag and drops that run (the gated two-pass
   //   fallback then redoes the whole partition).  gated: run only if *flag != 0.
@@ -103,7 +117,7 @@ __global__ void __launch_bounds__(kPartThreads)
   __shared__ uint32_t s_warp[kPartThreads / 32];
   const int parts = (int) fn.pmask + 1;
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
-  const size_t nfull = n / kPartTile;  // complete tiles travel through the TMA buffer, the ragged tail is loaded directly
+  // complete tiles travel through the TMA buffer (prefetched one tile ahead), ragged ones are loaded directly
   uint32_t phase = 0;
   if (TMA) {
     if (threadIdx.x == 0) {
@@ -111,18 +125,29 @@ __global__ void __launch_bounds__(kPartThreads)
       mbar_fence_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0 && (size_t) blockIdx.x < nfull) {
+    if (threadIdx.x == 0 && (size_t) blockIdx.x < ntiles && tile_rows(blockIdx.x, n, seg) == (uint32_t) kPartTile) {
       mbar_expect_tx(&s_bar, kPartTile * 8);
       tma_load_1d(s_in, keys + (size_t) blockIdx.x * kPartTile, kPartTile * 8, &s_bar);
     }
   }
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t tbase = tile * (size_t) kPartTile;
+    const uint32_t tile_n = tile_rows(tile, n, seg);  // CTA-uniform
+    const bool staged = TMA && tile_n == (uint32_t) kPartTile;
+    const size_t next = tile + gridDim.x;
+    const bool next_staged = TMA && next < ntiles && tile_rows(next, n, seg) == (uint32_t) kPartTile;
+    if (tile_n == 0) {
+      // slack tile of a segmented input: nothing to scatter.  No bulk copy is in flight (only complete tiles are staged) and
+      // the previous iteration ended behind a barrier with every read of the staging buffer fenced, so it can be refilled.
+      if (next_staged && threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, kPartTile * 8);
+        tma_load_1d(s_in, keys + next * (size_t) kPartTile, kPartTile * 8, &s_bar);
+      }
+      continue;
+    }
     for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
     uint64_t k[kPartItems];
     uint32_t p[kPartItems], r[kPartItems];
-    const size_t tbase = tile * (size_t) kPartTile;
-    const uint32_t tile_n = (uint32_t) (n - tbase < (size_t) kPartTile ? n - tbase : (size_t) kPartTile);  // CTA-uniform
-    const bool staged = TMA && tile < nfull;
     if (staged) {
       mbar_wait(&s_bar, phase);
       phase ^= 1u;
@@ -145,9 +170,9 @@ __global__ void __launch_bounds__(kPartThreads)
     // -- bar.sync alone is not enough (observed: whole 32-key warp slices replaced by the next tile's keys).
     if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (TMA && threadIdx.x == 0 && tile + gridDim.x < nfull) {
+    if (next_staged && threadIdx.x == 0) {
       mbar_expect_tx(&s_bar, kPartTile * 8);
-      tma_load_1d(s_in, keys + (tile + gridDim.x) * (size_t) kPartTile, kPartTile * 8, &s_bar);
+      tma_load_1d(s_in, keys + next * (size_t) kPartTile, kPartTile * 8, &s_bar);
     }
     // exclusive scan of the per-partition counts (parts <= kMaxParts = kBins * kPartThreads).  The global
     // range reservations (one atomicAdd per non-empty partition) are ISSUED here but only consumed after the
@@ -220,15 +245,15 @@ __global__ void __launch_bounds__(kPartThreads)
 template <bool PEERS>
 static int launch_scatter(const int64_t *d_keys, size_t n, PartFn fn, const unsigned long long *d_offsets, unsigned long long *d_cursors,
                           const ScatterDst &dst, size_t blocks, cudaStream_t st, unsigned long long cap_rows = 0, int *flag = nullptr,
-                          int gated = 0) {
+                          int gated = 0, SegIn seg = SegIn()) {
   const bool tma = (reinterpret_cast<uintptr_t>(d_keys) & 15) == 0;  // bulk copies need 16-byte alignment
   const size_t smem = (tma ? 2 : 1) * (size_t) kPartTile * sizeof(uint64_t) + (size_t) kPartTile * sizeof(uint16_t);
   if (tma) {
     CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated);
+    partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated, seg);
   } else {
     CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    partition_scatter_kernel<PEERS, false><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated);
+    partition_scatter_kernel<PEERS, false><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated, seg);
   }
   CC_CHECK_LAUNCH();
   return CC_OK;
@@ -257,7 +282,7 @@ __global__ void partition_seg_prefix_kernel(const unsigned long long *__restrict
 }
 
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
-                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st) {
+                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg) {
   const int parts = (int) fn.pmask + 1;
   CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
   CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
@@ -265,23 +290,30 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
   if (blocks == 0) blocks = 1;
   ScatterDst dst;
   dst.p[0] = d_out;
-  CC_TRY(launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0));
+  CC_TRY(launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
+  if (d_prefix) CC_TRY(seg_prefix_device(d_cursors, parts, cap_rows, seg_tile, d_prefix, st));
+  return CC_OK;
+}
+
+int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,
+                      cudaStream_t st) {
   partition_seg_prefix_kernel<<<1, 256, 0, st>>>(d_cursors, parts, cap_rows, seg_tile, d_prefix);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
 
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
-                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count, int *gate) {
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count, int *gate, SegIn seg,
+                     unsigned long long *d_total) {
   const int parts = (int) fn.pmask + 1;
   CC_CUDA(cudaMemsetAsync(d_counts, 0, parts * sizeof(unsigned long long), st));
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   if (blocks == 0) blocks = 1;
   if (n) {
-    partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_counts, gate);
+    partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, st>>>(d_keys, n, fn, d_counts, gate, seg);
     CC_CHECK_LAUNCH();
   }
-  partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors, gate);
+  partition_offsets_kernel<<<1, 256, 0, st>>>(d_counts, parts, d_offsets, d_cursors, gate, d_total);
   CC_CHECK_LAUNCH();
   if (after_count) {
     if (!*after_count) cudaEventCreate(after_count);
@@ -290,7 +322,7 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
   if (n) {
     ScatterDst dst;
     dst.p[0] = d_out;
-    CC_TRY(launch_scatter<false>(d_keys, n, fn, d_offsets, d_cursors, dst, blocks, st, 0, gate, gate ? 1 : 0));
+    CC_TRY(launch_scatter<false>(d_keys, n, fn, d_offsets, d_cursors, dst, blocks, st, 0, gate, gate ? 1 : 0, seg));
   }
   return CC_OK;
 }
@@ -310,7 +342,7 @@ int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t
   if (n == 0) return CC_OK;
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   partition_count_kernel<<<(unsigned) blocks, kPartThreads, 0, as_stream(s)>>>(d_keys, n, PartFn::high_bits(log2_parts),
-                                                                              (unsigned long long *) d_counts, nullptr);
+                                                                              (unsigned long long *) d_counts, nullptr, SegIn());
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -328,6 +360,20 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
   dst.p[0] = d_out;
   return launch_scatter<false>(d_keys, n, PartFn::high_bits(log2_parts), (const unsigned long long *) d_offsets, (unsigned long long *) d_cursors, dst,
                                blocks, as_stream(s));
+}
+
+// Single-pass partition by owner (high hash bits) into fixed regions of `region_capacity` rows: no histogram pass and no
+// host round trip -- d_counts[p] = rows of partition p, *d_overflow != 0 if a region overran (skewed keys: the result is
+// unusable, use the two-pass cc_partition_count + cc_partition_scatter instead).  This is the send side of the copy-engine
+// exchange: region p is then copied into peer p's receive buffer as one block.
+int cc_partition_single(const int64_t *d_keys, size_t n, int log2_parts, size_t region_capacity, uint64_t *d_counts, int *d_overflow,
+                        int64_t *d_out, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxParts, "log2_parts must be in [0, %d]", 9);
+  CC_REQUIRE(d_counts && d_overflow && d_out && (n == 0 || d_keys), "NULL argument");
+  CC_REQUIRE(region_capacity > 0, "region_capacity must be positive");
+  return partition_single_device(d_keys, n, PartFn::high_bits(log2_parts), region_capacity, (unsigned long long *) d_counts, d_overflow, 0,
+                                 nullptr, d_out, as_stream(s), SegIn());
 }
 
 static int g_peer_blocks = 0;  // 0 = fill the GPU; > 0 = CTA cap of the peer scatter (it is NVLink-bound)

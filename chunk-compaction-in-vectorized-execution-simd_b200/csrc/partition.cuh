@@ -38,16 +38,29 @@ struct PartFn {
   }
 };
 
+// Segmented INPUT column (the receive buffer of the copy-engine exchange, parallel.py): segment s holds counts[s] valid rows
+// at keys + s * cap, cap a multiple of kPartTile; the kernels then walk n = segments * cap rows and skip the slack.
+// cap == 0: plain dense input.
+struct SegIn {
+  const unsigned long long *counts = nullptr;
+  unsigned long long cap = 0;
+  int segments = 0;
+};
+
 // histogram + offsets + scatter on `st`; d_counts/d_offsets/d_cursors hold P entries each
 // after_count (optional): an event slot recorded between the histogram and the scatter (phase timing)
 // gate (optional): every kernel of the sequence only runs when *gate != 0 (device-side fallback switch)
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
-                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count = nullptr, int *gate = nullptr);
+                     unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count = nullptr, int *gate = nullptr,
+                     SegIn seg = SegIn(), unsigned long long *d_total = nullptr);  // d_total (optional): rows written, on the device
 
 // Single-pass partition (no histogram): partition p is scattered into the fixed region [p * cap_rows, (p + 1) * cap_rows) of
 // d_out; d_cursors[p] = rows written; *d_flag != 0 if some region overran (then the result is unusable and the caller's gated
 // two-pass fallback takes over); d_prefix[0 .. parts] = exclusive prefix of the per-partition tile counts (seg_tile rows each).
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
-                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st);
+                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg = SegIn());
+// d_prefix[0 .. parts] = exclusive prefix of ceil(min(d_cursors[p], cap_rows) / seg_tile) (the probe kernel's tile directory)
+int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,
+                      cudaStream_t st);
 
 }  // namespace ccb

@@ -838,8 +838,18 @@ static bool want_partitioned(const cc_ht *ht, size_t n, const uint64_t *d_out_ro
   return table_bytes >= ((size_t) 96 << 20) && n >= ((size_t) 1 << 22) && n >= table_bytes / 64;
 }
 
+// The two-pass partition of a SEGMENTED input writes a dense column whose row count only the device knows (ctl[3], tile
+// directory at ctl[4]): the probe reads it as one segment of capacity n.
+static void dense_rows_on_device(ProbeArgs &a, unsigned long long *ctl, size_t n) {
+  a.seg_prefix = reinterpret_cast<const uint32_t *>(ctl + 4);
+  a.seg_cursors = ctl + 3;
+  a.seg_cap = n;
+  a.seg_parts = 1;
+}
+
+// seg (optional): the key column is segmented (SegIn, partition.cuh) -- n is then segments * cap, an upper bound of the row count
 int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
-                       uint64_t *d_out_rowid, size_t cap, cc_probe_result *d_result, cudaStream_t st) {
+                       uint64_t *d_out_rowid, size_t cap, cc_probe_result *d_result, cudaStream_t st, SegIn seg = SegIn()) {
   ProbeArgs a;
   a.slots = ht->d_slots;
   a.dir = ht->d_dir;
@@ -874,7 +884,7 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
     // [8 ..) cursors | counts | offsets (parts each) | tile prefix (parts + 1 uint32), plus the partitioned keys
     unsigned long long *ctl = nullptr;
     int64_t *scratch = nullptr;
-    const size_t ctl_words = 8 + 4 * (size_t) parts + 8;
+    const size_t ctl_words = 8 + 4 * (size_t) parts + 8 + (size_t) seg.segments;
     CC_CUDA(cudaMallocAsync(&ctl, ctl_words * sizeof(unsigned long long), st));
     CC_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
     a.tile_counter = ctl;
@@ -899,7 +909,7 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
       profile_mark(0, st);
       if (single) {
         if (g_profile) profile_mark(1, st);
-        rc = partition_single_device(d_keys, n, fn, cap_rows, cursors, flag, kPbTile, prefix, scratch, st);
+        rc = partition_single_device(d_keys, n, fn, cap_rows, cursors, flag, kPbTile, prefix, scratch, st, seg);
         profile_mark(2, st);
         if (rc == CC_OK) {
           ProbeArgs b = a;
@@ -912,20 +922,24 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
           b.gate_want = 0;
           rc = dispatch_probe(g_mode_partitioned, ht, b, st);
         }
-        if (rc == CC_OK) rc = partition_device(d_keys, n, fn, counts, offsets, cursors, scratch, st, nullptr, flag);  // gated fallback
+        if (rc == CC_OK) rc = partition_device(d_keys, n, fn, counts, offsets, cursors, scratch, st, nullptr, flag, seg, ctl + 3);  // gated fallback
+        if (rc == CC_OK && seg.cap) rc = seg_prefix_device(ctl + 3, 1, n, kPbTile, reinterpret_cast<uint32_t *>(ctl + 4), st);
         if (rc == CC_OK) {
           ProbeArgs b = a;
           b.keys = scratch;
           b.tile_counter = ctl + 1;
+          if (seg.cap) dense_rows_on_device(b, ctl, n);
           b.gate = flag;
           b.gate_want = 1;
           rc = dispatch_probe(g_mode_partitioned, ht, b, st);
         }
       } else {
-        rc = partition_device(d_keys, n, fn, counts, offsets, cursors, scratch, st, g_profile ? &g_ev[1] : nullptr);
+        rc = partition_device(d_keys, n, fn, counts, offsets, cursors, scratch, st, g_profile ? &g_ev[1] : nullptr, nullptr, seg, ctl + 3);
+        if (rc == CC_OK && seg.cap) rc = seg_prefix_device(ctl + 3, 1, n, kPbTile, reinterpret_cast<uint32_t *>(ctl + 4), st);
         profile_mark(2, st);
         if (rc == CC_OK) {
           a.keys = scratch;
+          if (seg.cap) dense_rows_on_device(a, ctl, n);
           rc = dispatch_probe(g_mode_partitioned, ht, a, st);
         }
       }
@@ -934,7 +948,15 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
       cudaFreeAsync(scratch, st);
     } else {
       profile_mark(2, st);
-      rc = dispatch_probe(g_mode_direct, ht, a, st);
+      if (seg.cap) {  // probe the segmented column in place
+        uint32_t *prefix = reinterpret_cast<uint32_t *>(ctl + 8);
+        rc = seg_prefix_device(seg.counts, seg.segments, seg.cap, kPbTile, prefix, st);
+        a.seg_prefix = prefix;
+        a.seg_cursors = seg.counts;
+        a.seg_cap = seg.cap;
+        a.seg_parts = seg.segments;
+      }
+      if (rc == CC_OK) rc = dispatch_probe(g_mode_direct, ht, a, st);
       profile_mark(3, st);
       g_ev_valid = g_profile ? 1 : 0;
     }
@@ -986,6 +1008,20 @@ int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned) {
   g_mode_direct = mode_direct;
   g_mode_partitioned = mode_partitioned;
   return CC_OK;
+}
+
+int cc_probe_batch_segmented(const cc_ht *ht, const int64_t *d_keys, int n_segments, size_t segment_capacity, const uint64_t *d_segment_counts,
+                             int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity, cc_probe_result *d_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(ht && d_result && d_keys && d_segment_counts, "NULL argument");
+  CC_REQUIRE(n_segments >= 1 && n_segments <= kMaxParts, "n_segments must be in [1, %d]", kMaxParts);
+  CC_REQUIRE(segment_capacity > 0 && segment_capacity % kPartTile == 0, "segment_capacity must be a positive multiple of %d", kPartTile);
+  SegIn seg;
+  seg.counts = reinterpret_cast<const unsigned long long *>(d_segment_counts);
+  seg.cap = segment_capacity;
+  seg.segments = n_segments;
+  return probe_batch_device(ht, d_keys, (size_t) n_segments * segment_capacity, d_out_key, d_out_payload, nullptr, out_capacity, d_result,
+                            as_stream(s), seg);
 }
 
 int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,

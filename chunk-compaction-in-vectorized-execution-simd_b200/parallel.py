@@ -141,14 +141,131 @@ class PeerExchange:
         self._opened, self.local = [], []
 
 
+class CopyExchange:
+    """Exchange by copy engine: SM-free, host-sync-free, overlapped with the probe (NVLink 5 / NVSwitch).
+
+    A shuffle is split into a START and a FINISH half:
+      start  : ONE single-pass partition kernel (cc_partition_single) groups the keys by owner into fixed regions of a local
+               send buffer -- no histogram pass, the region fill counts stay on the device.  Then, on a COPY stream, region p is
+               copied as one block into slot [this rank] of owner p's receive buffer (CUDA IPC mapping, cudaMemcpyAsync: the
+               copy engines move it over NVLink without occupying a single SM), and the counts are all-gathered.
+      finish : wait for the own copies, then a stream-ordered all-reduce as the barrier ("every rank's copies have landed").
+    The receive buffer is a SEGMENTED column (one segment per sender, counts on the device) that cc_probe_batch_segmented
+    consumes as is -- the host never learns a count, so nothing ever blocks the launch queue.  PartitionedJoin.probe_pipelined
+    starts sub-batch b + 1 before it finishes sub-batch b: the copies of b + 1 run underneath the probe of b, and per key the
+    SMs only do the owner partition, the slice partition and the probe.  (The fused peer-scatter kernel of PeerExchange moves
+    the same bytes but needs every SM while it runs, so it cannot overlap a probe that also wants every SM.)
+    Cost: the regions are copied with their slack (12.5 % more NVLink bytes).  Heavily skewed keys overrun a region: this is
+    detected on the device and reported by check_overflow() -- use exchange="p2p" or "nccl" for such inputs."""
+
+    TILE = 4096  # region capacities are multiples of the partition kernel's tile
+
+    def __init__(self, pkg, max_rows: int, group=None, n_buffers: int = 3):
+        import ctypes as C
+
+        self.pkg, self.group = pkg, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.log2p = log2_exact(self.world)
+        self.n_buffers = n_buffers
+        self.step = 0
+        self.max_rows = int(max_rows)
+        per = (self.max_rows + self.world - 1) // self.world
+        self.cap = ((per + per // 8 + 2 * self.TILE + self.TILE - 1) // self.TILE) * self.TILE  # rows per (sender, owner) region
+        self.rows = self.cap * self.world
+        lib = pkg.lib()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.local, self.peers, self._opened = [], [], []
+        for _ in range(n_buffers):
+            ptr = C.c_void_p()
+            pkg._lib.check(lib.cc_malloc(C.byref(ptr), self.rows * 8))
+            handle = (C.c_ubyte * 64)()
+            pkg._lib.check(lib.cc_ipc_export(ptr, handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(ptr.value)
+                else:
+                    hb = (C.c_ubyte * 64).from_buffer_copy(h)
+                    q = C.c_void_p()
+                    pkg._lib.check(lib.cc_ipc_open(hb, C.byref(q)))
+                    ptrs.append(q.value)
+                    self._opened.append(q.value)
+            self.local.append(ptr.value)
+            self.peers.append(ptrs)
+        self.send = [torch.empty(self.rows, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.counts = [torch.zeros(self.world, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.matrix = [torch.zeros(self.world * self.world, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.mine = [torch.zeros(self.world, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.overflow = torch.zeros(n_buffers, dtype=torch.int32, device=dev)
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._copy_stream = torch.cuda.Stream()
+        self._copied = [None] * n_buffers
+        dist.barrier(group=group)
+
+    def start(self, keys: torch.Tensor) -> int:
+        """First half of shuffle k (returned): owner partition on the current stream, block copies on the copy stream."""
+        pkg, lib = self.pkg, self.pkg.lib()
+        n = keys.numel()
+        if n > self.max_rows:
+            raise ValueError(f"{n} keys exceed the {self.max_rows} rows per shuffle this exchange was sized for")
+        k = self.step
+        self.step += 1
+        b = k % self.n_buffers
+        main = torch.cuda.current_stream()
+        pkg.partition_single(keys, self.log2p, self.cap, out=self.send[b], counts=self.counts[b], overflow=self.overflow[b:b + 1])
+        parted = torch.cuda.Event()
+        parted.record(main)
+        dist.all_gather_into_tensor(self.matrix[b], self.counts[b], group=self.group)  # matrix[sender * P + owner]
+        self.mine[b].copy_(self.matrix[b].view(self.world, self.world)[:, self.rank])  # rows every sender delivers to this rank
+        cs = self._copy_stream
+        cs.wait_event(parted)
+        src = self.send[b].data_ptr()
+        block = self.cap * 8
+        for i in range(self.world):
+            p = (self.rank + i) % self.world  # stagger the destinations so that the ranks do not all hit the same peer at once
+            pkg._lib.check(lib.cc_memcpy_d2d(self.peers[b][p] + self.rank * block, src + p * block, block, cs.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(cs)
+        self._copied[b] = done
+        return k
+
+    def finish(self, k: int):
+        """Second half of shuffle k: returns (segmented receive column, segment capacity, device counts[P])."""
+        b = k % self.n_buffers
+        torch.cuda.current_stream().wait_event(self._copied[b])
+        dist.all_reduce(self._token, group=self.group)  # stream-ordered barrier: every rank's copies have landed
+        return self.pkg._wrap_ptr(self.local[b], self.rows, torch.int64), self.cap, self.mine[b]
+
+    def check_overflow(self) -> None:
+        """Raises if any shuffle since the last check overran a region (synchronises)."""
+        bad = int(self.overflow.sum().item())
+        self.overflow.zero_()
+        if bad:
+            raise RuntimeError("copy-engine exchange: a partition region overran (heavily skewed keys); use exchange='p2p' or 'nccl'")
+
+    def close(self) -> None:
+        lib = self.pkg.lib()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for q in self._opened:
+            lib.cc_ipc_close(q)
+        for p in self.local:
+            lib.cc_free(p)
+        self._opened, self.local = [], []
+
+
 class PartitionedJoin:
     """Build once, probe many times.  `pkg` is the product package (passed in to avoid a circular import)."""
 
     def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition",
                  exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0):
         """plan: "partition" (hash-partition both sides) or "broadcast" (replicate the build side).
-        exchange: "nccl" (scatter locally, then all_to_all_single) or "p2p" (PeerExchange: the scatter kernel
-        writes into the owners' buffers over NVLink); capacity_rows sizes the p2p receive buffers."""
+        exchange: "nccl" (scatter locally, then all_to_all_single), "p2p" (PeerExchange: the scatter kernel
+        writes into the owners' buffers over NVLink) or "ce" (CopyExchange: single-pass partition + copy-engine block
+        copies, overlapped with the probe by probe_pipelined; the build side then travels by all_to_all_single);
+        capacity_rows sizes the p2p receive buffers / the largest "ce" sub-batch."""
         self.pkg = pkg
         self.group = group
         self.world = dist.get_world_size(group)
@@ -156,6 +273,7 @@ class PartitionedJoin:
         self.log2p = log2_exact(self.world)
         self.plan = plan
         self.peer = PeerExchange(pkg, capacity_rows, group, peer_blocks=peer_blocks) if (exchange == "p2p" and plan == "partition") else None
+        self.copier = CopyExchange(pkg, capacity_rows, group) if (exchange == "ce" and plan == "partition") else None
         T = pkg.LPHashTable if kind == pkg.CC_HT_LP else pkg.HashTable
         if plan == "broadcast":
             n_local = torch.tensor([local_build_keys.numel()], dtype=torch.int64, device=local_build_keys.device)
@@ -192,7 +310,9 @@ class PartitionedJoin:
         (one cc_probe_result per sub-batch); outputs are written into n_sub equal slices of out_key/out_payload.
         Buffer safety: with 3 receive buffers a peer may only fill buffer k % 3 again at shuffle k + 3, i.e. after
         it passed barrier k + 2, which this rank enters only once its probe of sub-batch k is complete."""
-        assert self.peer is not None, "pipelined probing needs the peer-memory exchange"
+        if self.copier is not None:
+            return self._probe_pipelined_ce(local_probe_keys, n_sub, out_key, out_payload, results)
+        assert self.peer is not None, "pipelined probing needs the peer-memory or the copy-engine exchange"
         main = torch.cuda.current_stream()
         if not hasattr(self, "_xstream"):
             self._xstream = torch.cuda.Stream()
@@ -212,6 +332,22 @@ class PartitionedJoin:
             done = torch.cuda.Event()
             done.record(main)
             self._probe_done[k] = done
+
+    def _probe_pipelined_ce(self, local_probe_keys, n_sub, out_key, out_payload, results) -> None:
+        """Copy-engine variant: everything that needs SMs is enqueued on the CURRENT stream in the order
+        P(0) P(1) B(0) L(0) P(2) B(1) L(1) ...  (P = owner partition of a sub-batch, B = barrier, L = local slice partition +
+        probe) while the block copies C(b) run on the copy stream underneath L(b - 1).  Buffer safety with 3 rotating buffers:
+        P(k + 3) is enqueued behind B(k + 1), which completes only when every rank has entered it, i.e. after its L(k)."""
+        cx = self.copier
+        chunks = list(local_probe_keys.chunk(n_sub))
+        cap = out_key.numel() // n_sub
+        pending = [cx.start(chunks[0])]
+        for b in range(len(chunks)):
+            if b + 1 < len(chunks):
+                pending.append(cx.start(chunks[b + 1]))
+            recv, seg_cap, counts = cx.finish(pending[b])
+            self.table.probe_batch_segmented(recv, self.world, seg_cap, counts, capacity=cap, out_key=out_key[b * cap:(b + 1) * cap],
+                                             out_payload=out_payload[b * cap:(b + 1) * cap], result=results[b], sync=False)
 
     def probe(self, local_probe_keys: torch.Tensor, **kw) -> dict:
         """One probe pass: (partition + all-to-all unless broadcast plan) + local batch probe."""

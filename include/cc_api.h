@@ -190,6 +190,14 @@ typedef struct {
 
 int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
                    uint64_t *d_out_rowid, size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
+/* The same probe over a SEGMENTED key column: segment s holds d_segment_counts[s] keys at d_keys + s * segment_capacity
+ * (segment_capacity a multiple of 4096, at most 512 segments); the rows in a segment's slack are never read.  The counts
+ * live on the DEVICE, so a producer on the same stream -- the copy-engine exchange of the partitioned multi-GPU join, whose
+ * receive buffer has one segment per sender -- never has to report them to the host.  Same output contract as cc_probe_batch
+ * (new functionality; no row ids).                                                                          */
+int cc_probe_batch_segmented(const cc_ht *ht, const int64_t *d_keys, int n_segments, size_t segment_capacity,
+                             const uint64_t *d_segment_counts, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity,
+                             cc_probe_result *d_result, cc_stream_t stream);
 /* Probe strategy for tables far larger than L2 (process-wide):
  *   0 auto (default): partition the probe keys by table slice when the table is >= 96 MiB, the
  *     batch holds >= max(4 Mi, table_bytes / 64) keys (each 128-byte table line is revisited)
@@ -305,6 +313,13 @@ int cc_tuner_destroy(cc_tuner *t);
 int cc_partition_count(const int64_t *d_keys, size_t n, int log2_parts, uint64_t *d_counts, cc_stream_t stream);
 int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const uint64_t *d_offsets,
                          uint64_t *d_cursors, int64_t *d_out, cc_stream_t stream);
+/* Single-pass variant (no histogram, no host round trip): partition p is scattered into the fixed region
+ * d_out[p * region_capacity ...]; d_counts[p] = its rows; *d_overflow != 0 if a region overran (heavily skewed keys: the
+ * output is then unusable and the two-pass pair above must be used).  Send side of the copy-engine exchange: region p is
+ * then copied into peer p's receive buffer (cc_ipc_open) with cc_memcpy_d2d, which a copy engine executes over NVLink
+ * without occupying an SM.                                                                                              */
+int cc_partition_single(const int64_t *d_keys, size_t n, int log2_parts, size_t region_capacity, uint64_t *d_counts,
+                        int *d_overflow, int64_t *d_out, cc_stream_t stream);
 /* Fused scatter + exchange: partition p is written straight into h_peer_bufs[p], which may be the
  * receive buffer of ANOTHER GPU mapped through CUDA IPC (stores travel over NVLink / NVSwitch).
  * d_base[p] = first row of this rank's segment inside peer p's buffer (prefix over the senders of

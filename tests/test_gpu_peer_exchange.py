@@ -44,3 +44,83 @@ def test_pipelined_peer_exchange_matches_direct(ccb, pg, n_sub, peer_blocks):
         r = res.cpu().numpy().view(np.uint64).sum(axis=0, dtype=np.uint64)
         assert int(r[0]) == want_n and int(r[1]) == want_sum and int(r[2]) == want_sum, (rep, r)
     join.peer.close()
+
+
+@pytest.mark.parametrize("n_sub", [1, 2, 4, 5])
+def test_pipelined_copy_exchange_matches_direct(ccb, pg, n_sub):
+    """CopyExchange (single-pass partition + block copies + segmented probe) in a one-rank group: every code path except
+    the IPC mapping runs; several passes exercise the rotation of the three send / receive buffers."""
+    par = importlib.import_module(PKG_NAME + ".parallel")
+    n_build, n_probe = 1 << 22, 3 * (1 << 22) + 777
+    build = torch.arange(n_build, dtype=torch.int64, device="cuda")
+    join = par.PartitionedJoin(ccb, ccb.CC_HT_LP, build, plan="partition", exchange="ce", capacity_rows=-(-n_probe // n_sub))
+    keys = ccb.gen_keys_counter(n_probe, 7, 2 * n_build - 1)  # hit rate 1/2
+    hits = keys[keys < n_build]
+    want_n, want_sum = hits.numel(), int(hits.sum().item()) & ((1 << 64) - 1)
+    cap = (n_probe // n_sub + 4096) * n_sub
+    ok = torch.empty(cap, dtype=torch.int64, device="cuda")
+    op = torch.empty(cap, dtype=torch.int64, device="cuda")
+    res = torch.zeros((n_sub, 4), dtype=torch.int64, device="cuda")
+    for rep in range(4):
+        join.probe_pipelined(keys, n_sub, ok, op, res)
+        torch.cuda.synchronize()
+        r = res.cpu().numpy().view(np.uint64).sum(axis=0, dtype=np.uint64)
+        assert int(r[0]) == want_n and int(r[1]) == want_sum and int(r[2]) == want_sum and int(r[3]) == 0, (rep, r)
+    join.copier.check_overflow()
+    # the materialised rows of the sub-batches together are exactly the matching probe keys
+    per = cap // n_sub
+    rn = res.cpu().numpy().view(np.uint64)[:, 0].astype(np.int64)
+    got = torch.cat([ok[b * per: b * per + int(rn[b])] for b in range(n_sub)])
+    assert torch.equal(torch.sort(got)[0], torch.sort(hits)[0])
+    join.copier.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("strategy", [1, 2, 3])
+def test_probe_batch_segmented_equals_dense(ccb, kind, strategy):
+    """cc_probe_batch_segmented over ragged segments (empty, one row, full to capacity) == cc_probe_batch over the
+    concatenation, for the direct probe and both partitioned strategies, both table kinds."""
+    n_build = 1 << 21
+    T = ccb.LPHashTable if kind == 0 else ccb.HashTable
+    tab = T(n_build, 1)
+    seg_cap, fills = 4096 * 40, [4096 * 40, 0, 1, 4096 * 7 + 5, 123457, 4096 * 40 - 1, 4096, 99999]
+    col = torch.full((len(fills) * seg_cap,), 1, dtype=torch.int64, device="cuda")  # slack rows hold a MATCHING key: reading one changes the count
+    parts = []
+    for s, f in enumerate(fills):
+        k = ccb.gen_keys_counter(max(f, 1), 100 + s, 2 * n_build - 1)[:f]
+        col[s * seg_cap: s * seg_cap + f] = k
+        parts.append(k)
+    dense = torch.cat(parts)
+    counts = torch.tensor(fills, dtype=torch.int64, device="cuda")
+    ccb.set_probe_strategy(strategy, 4 << 20)
+    try:
+        want = tab.probe_batch(dense)
+        cap = dense.numel()
+        ok = torch.empty(cap, dtype=torch.int64, device="cuda")
+        op = torch.empty(cap, dtype=torch.int64, device="cuda")
+        got = tab.probe_batch_segmented(col, len(fills), seg_cap, counts, capacity=cap, out_key=ok, out_payload=op)
+    finally:
+        ccb.set_probe_strategy(0, 32 << 20)
+    for f in ("n_matches", "key_sum", "payload_sum", "overflow"):
+        assert got[f] == want[f], (f, got[f], want[f])
+    n = got["n_matches"]
+    assert torch.equal(torch.sort(ok[:n])[0], torch.sort(want["out_key"][:n])[0]) and torch.equal(torch.sort(op[:n])[0], torch.sort(ok[:n])[0])
+
+
+def test_partition_single_regions(ccb):
+    """cc_partition_single: fixed regions, device-side counts, overflow flag on skewed keys."""
+    n, log2p = (1 << 20) + 4321, 3
+    P = 1 << log2p
+    keys = ccb.gen_keys_counter(n, 5, (1 << 40) - 1)
+    cap = ((n // P) * 9 // 8 + 8192 + 4095) // 4096 * 4096
+    out, counts, flag = ccb.partition_single(keys, log2p, cap)
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0 and int(counts.sum().item()) == n
+    h = ccb.murmurhash64(keys)
+    pid = (h.view(torch.int64) >> (64 - log2p)) & (P - 1)
+    for p in range(P):
+        c = int(counts[p].item())
+        assert torch.equal(torch.sort(out[p * cap: p * cap + c])[0], torch.sort(keys[pid == p])[0])
+    same = torch.full((n,), 42, dtype=torch.int64, device="cuda")  # every key in one partition: the region must overrun
+    _, _, flag = ccb.partition_single(same, log2p, cap)
+    assert int(flag.item()) != 0
