@@ -353,6 +353,11 @@ class _TableBase:
             out.update(n_matches=int(r[0]), key_sum=int(r[1]), payload_sum=int(r[2]), overflow=int(r[3]))
         return out
 
+    def probe_stream(self, n_expected: int, *, capacity: int, out_key: Optional[torch.Tensor] = None,
+                     out_payload: Optional[torch.Tensor] = None, result: Optional[torch.Tensor] = None) -> "ProbeStream":
+        """cc_probe_stream_begin: an incremental probe of this table (add pieces, then finish)."""
+        return ProbeStream(self, n_expected, capacity, out_key, out_payload, result)
+
     def probe_batch_host(self, h_keys: np.ndarray, h_out_key: Optional[np.ndarray], h_out_payload: Optional[np.ndarray]) -> dict:
         """End-to-end probe with HOST buffers (cc_probe_batch_host): H2D + probe + D2H inside."""
         r = ProbeResult()
@@ -380,6 +385,42 @@ class _TableBase:
 
     def __del__(self):
         self.destroy()
+
+
+class ProbeStream:
+    """Incremental probe (cc_probe_stream_*): pieces of the key column are added as they arrive, one probe result."""
+
+    def __init__(self, table: "_TableBase", n_expected: int, capacity: int, out_key, out_payload, result):
+        self.result = result if result is not None else torch.zeros(4, dtype=torch.int64, device="cuda")
+        self.out_key, self.out_payload = out_key, out_payload
+        h = C.c_void_p()
+        L.check(lib().cc_probe_stream_begin(C.byref(h), table._h, n_expected, _ptr(out_key), _ptr(out_payload),
+                                            capacity if (out_key is not None or out_payload is not None) else 0, _ptr(self.result), _stream()))
+        self._h = h
+
+    def add(self, keys: torch.Tensor) -> None:
+        L.check(lib().cc_probe_stream_add(self._h, _ptr(keys) if keys.numel() else None, keys.numel(), 0, 0, None, _stream()))
+
+    def add_segmented(self, keys: torch.Tensor, n_segments: int, segment_capacity: int, segment_counts: torch.Tensor) -> None:
+        assert keys.numel() >= n_segments * segment_capacity and segment_counts.dtype == torch.int64
+        L.check(lib().cc_probe_stream_add(self._h, _ptr(keys), 0, n_segments, segment_capacity, _ptr(segment_counts), _stream()))
+
+    def finish(self, sync: bool = True) -> dict:
+        h, self._h = self._h, None
+        L.check(lib().cc_probe_stream_finish(h, _stream()))
+        out = {"result_tensor": self.result, "out_key": self.out_key, "out_payload": self.out_payload}
+        if sync:
+            r = self.result.cpu().numpy().view(np.uint64)
+            out.update(n_matches=int(r[0]), key_sum=int(r[1]), payload_sum=int(r[2]), overflow=int(r[3]))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib().cc_probe_stream_finish(self._h, None)
+            except Exception:
+                pass
+            self._h = None
 
 
 class HashTable(_TableBase):
@@ -578,9 +619,11 @@ def _chain_result_dict(r: ChainResult, J: int) -> dict:
 
 # ---- multi-GPU partitioning -----------------------------------------------------------------
 def partition_single(keys: torch.Tensor, log2_parts: int, region_capacity: int, out: Optional[torch.Tensor] = None,
-                     counts: Optional[torch.Tensor] = None, overflow: Optional[torch.Tensor] = None):
+                     counts: Optional[torch.Tensor] = None, overflow: Optional[torch.Tensor] = None, self_part: int = -1,
+                     self_out_ptr: Optional[int] = None):
     """cc_partition_single: single-pass hash partition into fixed regions of `region_capacity` rows.
-    Returns (out[P * region_capacity], counts[P] int64 device, overflow int32[1] device); nothing is synchronised."""
+    Returns (out[P * region_capacity], counts[P] int64 device, overflow int32[1] device); nothing is synchronised.
+    self_part / self_out_ptr: that partition is written to the buffer at self_out_ptr (same region offset) instead."""
     _ensure()
     P = 1 << log2_parts
     n = keys.numel()
@@ -590,7 +633,8 @@ def partition_single(keys: torch.Tensor, log2_parts: int, region_capacity: int, 
         counts = torch.zeros(P, dtype=torch.int64, device="cuda")
     if overflow is None:
         overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
-    L.check(lib().cc_partition_single(_ptr(keys) if n else None, n, log2_parts, region_capacity, _ptr(counts), _ptr(overflow), _ptr(out), _stream()))
+    L.check(lib().cc_partition_single(_ptr(keys) if n else None, n, log2_parts, region_capacity, _ptr(counts), _ptr(overflow), _ptr(out),
+                                      self_part if self_out_ptr else -1, self_out_ptr, _stream()))
     return out, counts, overflow
 
 

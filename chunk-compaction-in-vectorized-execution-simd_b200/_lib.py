@@ -118,6 +118,9 @@ SIGNATURES = {
     "cc_columns_to_rows": (_int, [_pvp, _vp, _sz, _sz, _vp, _vp]),
     "cc_probe_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
     "cc_probe_batch_segmented": (_int, [_vp, _vp, _int, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "cc_probe_stream_begin": (_int, [_pvp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "cc_probe_stream_add": (_int, [_vp, _vp, _sz, _int, _sz, _vp, _vp]),
+    "cc_probe_stream_finish": (_int, [_vp, _vp]),
     "cc_probe_set_strategy": (_int, [_int, _sz]),
     "cc_probe_set_cache_mode": (_int, [_int, _int]),
     "cc_probe_set_profiling": (_int, [_int]),
@@ -144,7 +147,7 @@ SIGNATURES = {
     "cc_partition_count": (_int, [_vp, _sz, _int, _vp, _vp]),
     "cc_partition_scatter": (_int, [_vp, _sz, _int, _vp, _vp, _vp, _vp]),
     "cc_partition_scatter_peers": (_int, [_vp, _sz, _int, _vp, _vp, _pvp, _vp]),
-    "cc_partition_single": (_int, [_vp, _sz, _int, _sz, _vp, _vp, _vp, _vp]),
+    "cc_partition_single": (_int, [_vp, _sz, _int, _sz, _vp, _vp, _vp, _int, _vp, _vp]),
     "cc_partition_set_peer_blocks": (_int, [_int]),
     "cc_ipc_export": (_int, [_vp, _vp]),
     "cc_ipc_open": (_int, [_vp, _pvp]),

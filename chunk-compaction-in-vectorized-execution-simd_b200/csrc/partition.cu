@@ -282,15 +282,26 @@ __global__ void partition_seg_prefix_kernel(const unsigned long long *__restrict
 }
 
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
-                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg) {
+                            int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg, bool accumulate,
+                            int self_part, int64_t *d_self_out) {
   const int parts = (int) fn.pmask + 1;
-  CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
-  CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  if (!accumulate) {
+    CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
+    CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  }
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   if (blocks == 0) blocks = 1;
   ScatterDst dst;
   dst.p[0] = d_out;
-  CC_TRY(launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
+  if (self_part >= 0 && d_self_out) {
+    // one partition goes to a different buffer at the same region offset (the copy-engine exchange: the rows this rank keeps
+    // are written straight into its own receive buffer instead of being copied there afterwards)
+    CC_REQUIRE(parts <= kMaxPeers && self_part < parts, "a redirected partition needs at most %d partitions", kMaxPeers);
+    for (int p = 0; p < parts; ++p) dst.p[p] = p == self_part ? d_self_out : d_out;
+    CC_TRY(launch_scatter<true>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
+  } else {
+    CC_TRY(launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
+  }
   if (d_prefix) CC_TRY(seg_prefix_device(d_cursors, parts, cap_rows, seg_tile, d_prefix, st));
   return CC_OK;
 }
@@ -367,13 +378,13 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
 // unusable, use the two-pass cc_partition_count + cc_partition_scatter instead).  This is the send side of the copy-engine
 // exchange: region p is then copied into peer p's receive buffer as one block.
 int cc_partition_single(const int64_t *d_keys, size_t n, int log2_parts, size_t region_capacity, uint64_t *d_counts, int *d_overflow,
-                        int64_t *d_out, cc_stream_t s) {
+                        int64_t *d_out, int self_part, int64_t *d_self_out, cc_stream_t s) {
   CC_TRY(require_device());
   CC_REQUIRE(log2_parts >= 0 && (1 << log2_parts) <= kMaxParts, "log2_parts must be in [0, %d]", 9);
   CC_REQUIRE(d_counts && d_overflow && d_out && (n == 0 || d_keys), "NULL argument");
   CC_REQUIRE(region_capacity > 0, "region_capacity must be positive");
   return partition_single_device(d_keys, n, PartFn::high_bits(log2_parts), region_capacity, (unsigned long long *) d_counts, d_overflow, 0,
-                                 nullptr, d_out, as_stream(s), SegIn());
+                                 nullptr, d_out, as_stream(s), SegIn(), false, self_part, d_self_out);
 }
 
 static int g_peer_blocks = 0;  // 0 = fill the GPU; > 0 = CTA cap of the peer scatter (it is NVLink-bound)

@@ -726,8 +726,9 @@ __global__ void __launch_bounds__(kPbThreads, CCB_LEAN_MIN_BLOCKS) probe_unique_
   }
 }
 
-__global__ void probe_finish_kernel(cc_probe_result *res, size_t cap) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = res->n_matches > cap ? 1 : 0;
+// region_flag (optional): partition overrun flag of an incremental probe -> overflow bit 1
+__global__ void probe_finish_kernel(cc_probe_result *res, size_t cap, const int *region_flag = nullptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = (res->n_matches > cap ? 1 : 0) | ((region_flag && *region_flag) ? 2 : 0);
 }
 
 template <int KIND, bool UNIQUE, int MODE, bool W32>
@@ -1008,6 +1009,152 @@ int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned) {
   g_mode_direct = mode_direct;
   g_mode_partitioned = mode_partitioned;
   return CC_OK;
+}
+
+// ---- incremental probe ---------------------------------------------------------------------------------------------
+// cc_probe_stream_*: the key column arrives in pieces (the sub-batches of a multi-GPU exchange) but is probed as ONE batch.
+// For a table beyond L2 every piece is scattered into the table-slice regions as it arrives (the regions fill up across
+// pieces) and the probe runs once at the end -- so the table is streamed from HBM once per batch, not once per piece, while
+// the slice partition of piece b still overlaps the exchange of piece b + 1.  For a small table every piece is probed at once.
+struct cc_probe_stream {
+  const cc_ht *ht = nullptr;
+  ProbeArgs a;
+  bool part = false;
+  int parts = 0;
+  PartFn fn;
+  unsigned long long cap_rows = 0;
+  unsigned long long *ctl = nullptr;
+  int64_t *scratch = nullptr;
+};
+
+int cc_probe_stream_begin(cc_probe_stream **out, const cc_ht *ht, size_t n_expected, int64_t *d_out_key, int64_t *d_out_payload,
+                          size_t out_capacity, cc_probe_result *d_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(out && ht && d_result, "NULL argument");
+  cudaStream_t st = as_stream(s);
+  cc_probe_stream *h = new cc_probe_stream();
+  h->ht = ht;
+  ProbeArgs &a = h->a;
+  a.slots = ht->d_slots;
+  a.dir = ht->d_dir;
+  a.ckeys = ht->d_ckeys;
+  a.mask = ht->mask;
+  a.keys = nullptr;
+  a.n = 0;
+  a.out_key = d_out_key;
+  a.out_payload = d_out_payload;
+  a.out_rowid = nullptr;
+  a.cap = (d_out_key || d_out_payload) ? out_capacity : 0;
+  a.res = d_result;
+  a.tile_counter = nullptr;
+  a.seg_prefix = nullptr;
+  a.seg_cursors = nullptr;
+  a.seg_cap = 0;
+  a.seg_parts = 0;
+  a.gate = nullptr;
+  a.gate_want = 0;
+  cudaError_t e = cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st);
+  h->part = e == cudaSuccess && want_partitioned(ht, n_expected, nullptr);
+  if (e == cudaSuccess && h->part) {
+    const size_t table_bytes = ht->kind == CC_HT_LP ? ht->n_slots * 8 : ht->n_slots * 8 + ht->n_keys * 8;
+    const int log2_slots = log2_floor(ht->n_slots);
+    int log2p = log2_floor((table_bytes + g_slice_bytes - 1) / g_slice_bytes);
+    if ((size_t) 1 << log2p < (table_bytes + g_slice_bytes - 1) / g_slice_bytes) ++log2p;
+    if (log2p > log2_floor(kMaxParts)) log2p = log2_floor(kMaxParts);
+    if (log2p > log2_slots) log2p = log2_slots;
+    if (log2p < 1) log2p = 1;
+    h->parts = 1 << log2p;
+    h->fn = PartFn::slot_bits(ht->mask, log2_slots, log2p);
+    const size_t per = n_expected / h->parts;
+    h->cap_rows = (per + per / 8 + 2 * (size_t) kPartTile + kPbTile - 1) / kPbTile * kPbTile;
+  }
+  // control words: [0] tile counter, [2] region overrun flag, [8 ..) cursors (parts) | tile prefix (parts + 1 uint32)
+  const size_t ctl_words = 8 + 2 * (size_t) h->parts + 8;
+  if (e == cudaSuccess) e = cudaMallocAsync(&h->ctl, ctl_words * sizeof(unsigned long long), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->ctl, 0, ctl_words * sizeof(unsigned long long), st);
+  if (e == cudaSuccess && h->part) e = cudaMallocAsync(&h->scratch, (size_t) h->parts * h->cap_rows * sizeof(int64_t), st);
+  if (e != cudaSuccess) {
+    set_error("cc_probe_stream_begin: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    if (h->ctl) cudaFreeAsync(h->ctl, st);
+    delete h;
+    return e == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA;
+  }
+  *out = h;
+  return CC_OK;
+}
+
+// one piece: dense (n_segments == 0: d_keys[0 .. n)) or segmented (n ignored: n_segments x segment_capacity rows, counts on the device)
+int cc_probe_stream_add(cc_probe_stream *h, const int64_t *d_keys, size_t n, int n_segments, size_t segment_capacity,
+                        const uint64_t *d_segment_counts, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(h, "NULL argument");
+  cudaStream_t st = as_stream(s);
+  SegIn seg;
+  if (n_segments) {
+    CC_REQUIRE(d_keys && d_segment_counts, "NULL argument");
+    CC_REQUIRE(n_segments >= 1 && n_segments <= kMaxParts, "n_segments must be in [1, %d]", kMaxParts);
+    CC_REQUIRE(segment_capacity > 0 && segment_capacity % kPartTile == 0, "segment_capacity must be a positive multiple of %d", kPartTile);
+    seg.counts = reinterpret_cast<const unsigned long long *>(d_segment_counts);
+    seg.cap = segment_capacity;
+    seg.segments = n_segments;
+    n = (size_t) n_segments * segment_capacity;
+  }
+  if (n == 0) return CC_OK;
+  CC_REQUIRE(d_keys, "d_keys is NULL");
+  if (h->part)  // scatter into the slice regions, which keep filling up
+    return partition_single_device(d_keys, n, h->fn, h->cap_rows, h->ctl + 8, reinterpret_cast<int *>(h->ctl + 2), 0, nullptr, h->scratch, st, seg,
+                                   true);
+  // small table: probe the piece right away; the output rows continue behind those of the earlier pieces
+  ProbeArgs a = h->a;
+  a.keys = d_keys;
+  a.n = n;
+  a.tile_counter = h->ctl;
+  CC_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(unsigned long long), st));
+  if (seg.cap) {
+    uint32_t *prefix = reinterpret_cast<uint32_t *>(h->ctl + 8);
+    CC_REQUIRE(n_segments <= 16, "a small-table incremental probe takes at most 16 segments per piece");
+    CC_TRY(seg_prefix_device(seg.counts, seg.segments, seg.cap, kPbTile, prefix, st));
+    a.seg_prefix = prefix;
+    a.seg_cursors = seg.counts;
+    a.seg_cap = seg.cap;
+    a.seg_parts = seg.segments;
+  }
+  return dispatch_probe(g_mode_direct, h->ht, a, st);
+}
+
+// probes what the regions hold, closes the result (overflow bit 0: out_capacity too small, bit 1: a slice region overran --
+// heavily skewed keys, use cc_probe_batch) and releases the handle
+int cc_probe_stream_finish(cc_probe_stream *h, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(h, "NULL argument");
+  cudaStream_t st = as_stream(s);
+  int rc = CC_OK;
+  if (h->part) {
+    unsigned long long *cursors = h->ctl + 8;
+    uint32_t *prefix = reinterpret_cast<uint32_t *>(h->ctl + 8 + h->parts);
+    rc = seg_prefix_device(cursors, h->parts, h->cap_rows, kPbTile, prefix, st);
+    if (rc == CC_OK) {
+      ProbeArgs a = h->a;
+      a.keys = h->scratch;
+      a.n = (size_t) h->parts * h->cap_rows;
+      a.tile_counter = h->ctl;
+      a.seg_prefix = prefix;
+      a.seg_cursors = cursors;
+      a.seg_cap = h->cap_rows;
+      a.seg_parts = h->parts;
+      rc = dispatch_probe(g_mode_partitioned, h->ht, a, st);
+    }
+  }
+  if (rc == CC_OK) {
+    probe_finish_kernel<<<1, 32, 0, st>>>(h->a.res, h->a.cap, h->part ? reinterpret_cast<const int *>(h->ctl + 2) : nullptr);
+    note_launch();
+    if (cudaGetLastError() != cudaSuccess) rc = CC_ERR_CUDA;
+  }
+  if (h->scratch) cudaFreeAsync(h->scratch, st);
+  cudaFreeAsync(h->ctl, st);
+  delete h;
+  return rc;
 }
 
 int cc_probe_batch_segmented(const cc_ht *ht, const int64_t *d_keys, int n_segments, size_t segment_capacity, const uint64_t *d_segment_counts,

@@ -214,7 +214,9 @@ class CopyExchange:
         self.step += 1
         b = k % self.n_buffers
         main = torch.cuda.current_stream()
-        pkg.partition_single(keys, self.log2p, self.cap, out=self.send[b], counts=self.counts[b], overflow=self.overflow[b:b + 1])
+        # the rows this rank keeps go straight into slot [rank] of its own receive buffer (same region offset rank * cap)
+        pkg.partition_single(keys, self.log2p, self.cap, out=self.send[b], counts=self.counts[b], overflow=self.overflow[b:b + 1],
+                             self_part=self.rank if self.world <= 16 else -1, self_out_ptr=self.local[b])
         parted = torch.cuda.Event()
         parted.record(main)
         dist.all_gather_into_tensor(self.matrix[b], self.counts[b], group=self.group)  # matrix[sender * P + owner]
@@ -223,7 +225,7 @@ class CopyExchange:
         cs.wait_event(parted)
         src = self.send[b].data_ptr()
         block = self.cap * 8
-        for i in range(self.world):
+        for i in range(0 if self.world > 16 else 1, self.world):
             p = (self.rank + i) % self.world  # stagger the destinations so that the ranks do not all hit the same peer at once
             pkg._lib.check(lib.cc_memcpy_d2d(self.peers[b][p] + self.rank * block, src + p * block, block, cs.cuda_stream))
         done = torch.cuda.Event()
@@ -335,19 +337,42 @@ class PartitionedJoin:
 
     def _probe_pipelined_ce(self, local_probe_keys, n_sub, out_key, out_payload, results) -> None:
         """Copy-engine variant: everything that needs SMs is enqueued on the CURRENT stream in the order
-        P(0) P(1) B(0) L(0) P(2) B(1) L(1) ...  (P = owner partition of a sub-batch, B = barrier, L = local slice partition +
-        probe) while the block copies C(b) run on the copy stream underneath L(b - 1).  Buffer safety with 3 rotating buffers:
-        P(k + 3) is enqueued behind B(k + 1), which completes only when every rank has entered it, i.e. after its L(k)."""
+        P(0) P(1) B(0) S(0) P(2) B(1) S(1) ... B(n-1) S(n-1) PROBE  (P = owner partition of a sub-batch, B = barrier, S = scatter
+        of the received sub-batch into the table-slice regions of ONE incremental probe, cc_probe_stream_*) while the block
+        copies C(b) run on the copy stream underneath S(b - 1) / P(b + 1).  The table is streamed once per call, not once per
+        sub-batch.  Only results[0] is written (one dense output over all of out_key / out_payload).
+        Buffer safety with 3 rotating buffers: P(k + 3) is enqueued behind B(k + 1), which completes only when every rank has
+        entered it, i.e. after its S(k)."""
+        import os
         cx = self.copier
         chunks = list(local_probe_keys.chunk(n_sub))
-        cap = out_key.numel() // n_sub
+        trace = [] if os.environ.get("CCB_CE_TRACE") else None  # evidence switch: CUDA-event timeline of one call (synchronises)
+
+        def mark(name):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                trace.append((name, e))
+
+        mark("begin")
+        n_local = local_probe_keys.numel()
+        stream = self.table.probe_stream(n_local + n_local // 16 + (1 << 16), capacity=out_key.numel(), out_key=out_key, out_payload=out_payload,
+                                         result=results[0])
         pending = [cx.start(chunks[0])]
+        mark("P0")
         for b in range(len(chunks)):
             if b + 1 < len(chunks):
                 pending.append(cx.start(chunks[b + 1]))
+                mark(f"P{b + 1}")
             recv, seg_cap, counts = cx.finish(pending[b])
-            self.table.probe_batch_segmented(recv, self.world, seg_cap, counts, capacity=cap, out_key=out_key[b * cap:(b + 1) * cap],
-                                             out_payload=out_payload[b * cap:(b + 1) * cap], result=results[b], sync=False)
+            mark(f"B{b}")
+            stream.add_segmented(recv, self.world, seg_cap, counts)
+            mark(f"S{b}")
+        stream.finish(sync=False)
+        mark("PROBE")
+        if trace is not None and self.rank == 0:
+            torch.cuda.synchronize()
+            print("ce timeline (ms since begin): " + "  ".join(f"{n}={trace[0][1].elapsed_time(e):.2f}" for n, e in trace[1:]), flush=True)
 
     def probe(self, local_probe_keys: torch.Tensor, **kw) -> dict:
         """One probe pass: (partition + all-to-all unless broadcast plan) + local batch probe."""

@@ -198,6 +198,20 @@ int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_
 int cc_probe_batch_segmented(const cc_ht *ht, const int64_t *d_keys, int n_segments, size_t segment_capacity,
                              const uint64_t *d_segment_counts, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity,
                              cc_probe_result *d_result, cc_stream_t stream);
+/* Incremental probe: the key column arrives in pieces (the sub-batches of a multi-GPU exchange) and is probed as ONE batch.
+ *   begin : fixes the table, the dense output columns (same contract as cc_probe_batch) and the expected total row count
+ *   add   : one piece, dense (n_segments == 0: d_keys[0 .. n)) or segmented (n ignored; layout as in cc_probe_batch_segmented)
+ *   finish: completes the probe, writes *d_result and releases the handle.  overflow bit 0: out_capacity too small;
+ *           bit 1: heavily skewed keys overran a table-slice region (use cc_probe_batch for such inputs).
+ * For a table beyond L2 every piece is scattered into the table-slice regions as it arrives and the table is streamed from
+ * HBM once per batch instead of once per piece; a small table is probed piece by piece.  All calls must use one stream
+ * (new functionality).                                                                                        */
+typedef struct cc_probe_stream cc_probe_stream;
+int cc_probe_stream_begin(cc_probe_stream **out, const cc_ht *ht, size_t n_expected, int64_t *d_out_key, int64_t *d_out_payload,
+                          size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
+int cc_probe_stream_add(cc_probe_stream *h, const int64_t *d_keys, size_t n, int n_segments, size_t segment_capacity,
+                        const uint64_t *d_segment_counts, cc_stream_t stream);
+int cc_probe_stream_finish(cc_probe_stream *h, cc_stream_t stream);
 /* Probe strategy for tables far larger than L2 (process-wide):
  *   0 auto (default): partition the probe keys by table slice when the table is >= 96 MiB, the
  *     batch holds >= max(4 Mi, table_bytes / 64) keys (each 128-byte table line is revisited)
@@ -317,9 +331,10 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
  * d_out[p * region_capacity ...]; d_counts[p] = its rows; *d_overflow != 0 if a region overran (heavily skewed keys: the
  * output is then unusable and the two-pass pair above must be used).  Send side of the copy-engine exchange: region p is
  * then copied into peer p's receive buffer (cc_ipc_open) with cc_memcpy_d2d, which a copy engine executes over NVLink
- * without occupying an SM.                                                                                              */
+ * without occupying an SM.  self_part >= 0 (needs <= 16 partitions): that one partition is written to d_self_out at the
+ * same region offset instead -- the rows a rank keeps go straight into its own receive buffer.                                                                                              */
 int cc_partition_single(const int64_t *d_keys, size_t n, int log2_parts, size_t region_capacity, uint64_t *d_counts,
-                        int *d_overflow, int64_t *d_out, cc_stream_t stream);
+                        int *d_overflow, int64_t *d_out, int self_part, int64_t *d_self_out, cc_stream_t stream);
 /* Fused scatter + exchange: partition p is written straight into h_peer_bufs[p], which may be the
  * receive buffer of ANOTHER GPU mapped through CUDA IPC (stores travel over NVLink / NVSwitch).
  * d_base[p] = first row of this rank's segment inside peer p's buffer (prefix over the senders of

@@ -57,7 +57,7 @@ def test_pipelined_copy_exchange_matches_direct(ccb, pg, n_sub):
     keys = ccb.gen_keys_counter(n_probe, 7, 2 * n_build - 1)  # hit rate 1/2
     hits = keys[keys < n_build]
     want_n, want_sum = hits.numel(), int(hits.sum().item()) & ((1 << 64) - 1)
-    cap = (n_probe // n_sub + 4096) * n_sub
+    cap = n_probe
     ok = torch.empty(cap, dtype=torch.int64, device="cuda")
     op = torch.empty(cap, dtype=torch.int64, device="cuda")
     res = torch.zeros((n_sub, 4), dtype=torch.int64, device="cuda")
@@ -67,12 +67,62 @@ def test_pipelined_copy_exchange_matches_direct(ccb, pg, n_sub):
         r = res.cpu().numpy().view(np.uint64).sum(axis=0, dtype=np.uint64)
         assert int(r[0]) == want_n and int(r[1]) == want_sum and int(r[2]) == want_sum and int(r[3]) == 0, (rep, r)
     join.copier.check_overflow()
-    # the materialised rows of the sub-batches together are exactly the matching probe keys
-    per = cap // n_sub
-    rn = res.cpu().numpy().view(np.uint64)[:, 0].astype(np.int64)
-    got = torch.cat([ok[b * per: b * per + int(rn[b])] for b in range(n_sub)])
-    assert torch.equal(torch.sort(got)[0], torch.sort(hits)[0])
+    # the materialised rows are exactly the matching probe keys (one dense output over all sub-batches)
+    assert torch.equal(torch.sort(ok[:want_n])[0], torch.sort(hits)[0]) and torch.equal(torch.sort(op[:want_n])[0], torch.sort(hits)[0])
     join.copier.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("strategy", [1, 2])
+def test_probe_stream_equals_one_batch(ccb, kind, strategy):
+    """cc_probe_stream_*: dense and segmented pieces added one by one == cc_probe_batch over their concatenation (small-table
+    path: every piece probed at once; large-table path: pieces scattered into the slice regions, one probe at the end)."""
+    n_build = 1 << 21
+    T = ccb.LPHashTable if kind == 0 else ccb.HashTable
+    tab = T(n_build, 1)
+    seg_cap, fills = 4096 * 16, [4096 * 16, 0, 777, 4096 * 3 + 1]
+    seg_col = torch.full((len(fills) * seg_cap,), 1, dtype=torch.int64, device="cuda")
+    pieces = [ccb.gen_keys_counter(n, 50 + i, 2 * n_build - 1) for i, n in enumerate([300000, 1, 123456])]
+    seg_parts = []
+    for s, f in enumerate(fills):
+        k = ccb.gen_keys_counter(max(f, 1), 90 + s, 2 * n_build - 1)[:f]
+        seg_col[s * seg_cap: s * seg_cap + f] = k
+        seg_parts.append(k)
+    dense = torch.cat(pieces + seg_parts)
+    counts = torch.tensor(fills, dtype=torch.int64, device="cuda")
+    ccb.set_probe_strategy(strategy, 4 << 20)
+    try:
+        want = tab.probe_batch(dense)
+        cap = dense.numel()
+        ok = torch.empty(cap, dtype=torch.int64, device="cuda")
+        op = torch.empty(cap, dtype=torch.int64, device="cuda")
+        st = tab.probe_stream(dense.numel(), capacity=cap, out_key=ok, out_payload=op)
+        st.add(pieces[0])
+        st.add_segmented(seg_col, len(fills), seg_cap, counts)
+        st.add(pieces[1])
+        st.add(pieces[2])
+        st.add(pieces[2][:0])
+        got = st.finish()
+    finally:
+        ccb.set_probe_strategy(0, 32 << 20)
+    for f in ("n_matches", "key_sum", "payload_sum", "overflow"):
+        assert got[f] == want[f], (f, got[f], want[f])
+    n = got["n_matches"]
+    assert torch.equal(torch.sort(ok[:n])[0], torch.sort(want["out_key"][:n])[0]) and torch.equal(torch.sort(op[:n])[0], torch.sort(ok[:n])[0])
+
+
+def test_probe_stream_reports_region_overrun(ccb):
+    """Heavily skewed keys overrun a slice region of the incremental probe: reported as overflow bit 1, never silently wrong."""
+    tab = ccb.LPHashTable(1 << 21, 1)
+    same = torch.full((1 << 20,), 42, dtype=torch.int64, device="cuda")
+    ccb.set_probe_strategy(2, 4 << 20)
+    try:
+        st = tab.probe_stream(same.numel(), capacity=same.numel(), out_key=torch.empty_like(same), out_payload=torch.empty_like(same))
+        st.add(same)
+        got = st.finish()
+    finally:
+        ccb.set_probe_strategy(0, 32 << 20)
+    assert got["overflow"] & 2
 
 
 @pytest.mark.parametrize("kind", [0, 1])
@@ -113,9 +163,13 @@ def test_partition_single_regions(ccb):
     P = 1 << log2p
     keys = ccb.gen_keys_counter(n, 5, (1 << 40) - 1)
     cap = ((n // P) * 9 // 8 + 8192 + 4095) // 4096 * 4096
-    out, counts, flag = ccb.partition_single(keys, log2p, cap)
+    other = torch.full((P * cap,), -9, dtype=torch.int64, device="cuda")
+    out, counts, flag = ccb.partition_single(keys, log2p, cap, self_part=5, self_out_ptr=other.data_ptr())  # partition 5 is redirected
     torch.cuda.synchronize()
     assert int(flag.item()) == 0 and int(counts.sum().item()) == n
+    c5 = int(counts[5].item())
+    assert int((other != -9).sum().item()) == c5 and bool((other[5 * cap: 5 * cap + c5] != -9).all())
+    out[5 * cap: 5 * cap + c5] = other[5 * cap: 5 * cap + c5]
     h = ccb.murmurhash64(keys)
     pid = (h.view(torch.int64) >> (64 - log2p)) & (P - 1)
     for p in range(P):
