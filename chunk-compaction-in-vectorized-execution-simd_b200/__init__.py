@@ -278,17 +278,69 @@ class ScanStructure:
 class _TableBase:
     kind = -1
 
-    def __init__(self, n_rhs_tuples: Optional[int] = None, chunk_factor: int = 1, *, keys=None, flags: int = CC_BUILD_ORDERED):
+    def __init__(self, n_rhs_tuples: Optional[int] = None, chunk_factor: int = 1, *, keys=None, flags: int = CC_BUILD_ORDERED,
+                 payload=None, keep_payload: bool = False):
         """HashTable(n_rhs_tuples, chunk_factor) like the reference (chaining_ht.h:88), or keys=... for explicit
-        build keys (the reference has no external build-input API)."""
+        build keys (the reference has no external build-input API).
+        Payload columns: payload=[col, ...] with keys=..., or keep_payload=True to keep the column the
+        reference generates and drops (payload of build row i = i + 10000000, chaining_ht.cpp:21)."""
         _ensure()
         h = C.c_void_p()
         if keys is not None:
             k = _i64(keys)
             L.check(lib().cc_ht_build(C.byref(h), self.kind, _ptr(k) if k.numel() else None, k.numel(), flags, _stream()))
+            self._h = h.value
+            if payload is not None:
+                self.attach_payload(k, payload)
+        elif keep_payload:
+            L.check(lib().cc_ht_build_reference_payload(C.byref(h), self.kind, int(n_rhs_tuples), int(chunk_factor), _stream()))
+            self._h = h.value
         else:
             L.check(lib().cc_ht_build_reference(C.byref(h), self.kind, int(n_rhs_tuples), int(chunk_factor), _stream()))
-        self._h = h.value
+            self._h = h.value
+
+    def attach_payload(self, build_keys, payload_cols) -> None:
+        """cc_ht_attach_payload: keep int64 payload columns (one value per build row) next to the keys."""
+        k = _i64(build_keys)
+        cols = [_i64(c) for c in payload_cols]
+        assert all(c.numel() == k.numel() for c in cols)
+        arr = (C.c_void_p * len(cols))(*[_ptr(c) if c.numel() else None for c in cols])
+        L.check(lib().cc_ht_attach_payload(self._h, _ptr(k) if k.numel() else None, arr, len(cols), _stream()))
+
+    def payload_cols(self) -> int:
+        return int(lib().cc_ht_payload_cols(self._h))
+
+    def export_payload(self) -> List[np.ndarray]:
+        """payload columns in table order (LP: one row per slot; chain: chain order)"""
+        i = self.info()
+        rows = i.n_slots if self.kind == CC_HT_LP else i.n_keys
+        cols = [np.zeros(max(rows, 1), dtype=np.int64) for _ in range(self.payload_cols())]
+        arr = (C.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+        L.check(lib().cc_ht_export_payload(self._h, arr))
+        return [c[:rows] for c in cols]
+
+    def probe_batch_payload(self, keys: torch.Tensor, *, capacity: Optional[int] = None, n_out_cols: Optional[int] = None,
+                            materialize: bool = True, rowid: bool = False, sync: bool = True) -> dict:
+        """cc_probe_batch_payload: result rows (probe key, matched build key, payload columns of the matched build row)."""
+        n = keys.numel()
+        cap = capacity if capacity is not None else n
+        npay = self.payload_cols()
+        nout = npay if n_out_cols is None else n_out_cols
+        new = lambda: torch.empty(max(cap, 1), dtype=torch.int64, device="cuda")
+        out_key = new() if materialize else None
+        out_build = new() if materialize else None
+        out_cols = [new() for _ in range(nout)] if materialize else []
+        out_rowid = new() if rowid else None
+        result = torch.zeros(4 + L.CC_MAX_PAYLOAD_COLS, dtype=torch.int64, device="cuda")
+        arr = (C.c_void_p * max(len(out_cols), 1))(*[_ptr(c) for c in out_cols])
+        L.check(lib().cc_probe_batch_payload(self._h, _ptr(keys) if n else None, n, _ptr(out_key), _ptr(out_build), arr, len(out_cols),
+                                             _ptr(out_rowid), cap if (materialize or rowid) else 0, _ptr(result), _stream()))
+        out = {"result_tensor": result, "out_key": out_key, "out_build_key": out_build, "out_cols": out_cols, "out_rowid": out_rowid}
+        if sync:
+            r = result.cpu().numpy().view(np.uint64)
+            out.update(n_matches=int(r[0]), key_sum=int(r[1]), payload_sum=int(r[2]), overflow=int(r[3]),
+                       col_sum=[int(x) for x in r[4:4 + npay]])
+        return out
 
     @classmethod
     def import_slots(cls, slots: np.ndarray, n_keys: int) -> "_TableBase":

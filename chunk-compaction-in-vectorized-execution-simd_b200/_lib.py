@@ -62,6 +62,19 @@ class ProbeResult(C.Structure):
     ]
 
 
+CC_MAX_PAYLOAD_COLS = 4
+
+
+class ProbePayloadResult(C.Structure):
+    _fields_ = [
+        ("n_matches", C.c_uint64),
+        ("key_sum", C.c_uint64),
+        ("payload_sum", C.c_uint64),
+        ("overflow", C.c_uint64),
+        ("col_sum", C.c_uint64 * CC_MAX_PAYLOAD_COLS),
+    ]
+
+
 class ChainResult(C.Structure):
     _fields_ = [
         ("n_tuples", C.c_uint64),
@@ -102,6 +115,10 @@ SIGNATURES = {
     "cc_ht_build": (_int, [_pvp, _int, _vp, _sz, _int, _vp]),
     "cc_ht_build_reference": (_int, [_pvp, _int, _sz, _sz, _vp]),
     "cc_ht_import_lp": (_int, [_pvp, _vp, _sz, _sz, _vp]),
+    "cc_ht_attach_payload": (_int, [_vp, _vp, _pvp, _sz, _vp]),
+    "cc_ht_build_reference_payload": (_int, [_pvp, _int, _sz, _sz, _vp]),
+    "cc_ht_payload_cols": (_sz, [_vp]),
+    "cc_ht_export_payload": (_int, [_vp, _pvp]),
     "cc_ht_get_info": (_int, [_vp, C.POINTER(HtInfo)]),
     "cc_ht_export_lp": (_int, [_vp, _vp]),
     "cc_ht_export_chain": (_int, [_vp, _vp, _vp, _vp]),
@@ -117,6 +134,7 @@ SIGNATURES = {
     "cc_rows_to_columns": (_int, [_vp, _sz, _sz, _pvp, _vp]),
     "cc_columns_to_rows": (_int, [_pvp, _vp, _sz, _sz, _vp, _vp]),
     "cc_probe_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "cc_probe_batch_payload": (_int, [_vp, _vp, _sz, _vp, _vp, _pvp, _sz, _vp, _sz, _vp, _vp]),
     "cc_probe_batch_segmented": (_int, [_vp, _vp, _int, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
     "cc_probe_stream_begin": (_int, [_pvp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "cc_probe_stream_add": (_int, [_vp, _vp, _sz, _int, _sz, _vp, _vp]),

@@ -118,4 +118,7 @@ struct cc_ht {
   int has_duplicates;
   size_t max_chain;
   size_t bytes;
+  // payload columns: d_pay[c][i] belongs to the key at index i (LP: slot, chain: chain position)
+  int n_pay;
+  int64_t *d_pay[CC_MAX_PAYLOAD_COLS];
 };

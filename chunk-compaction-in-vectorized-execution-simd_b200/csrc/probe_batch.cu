@@ -31,6 +31,7 @@
 //     (L2-resident 16 MiB gather: 290 G/s with <= 16 KiB smem per CTA, 138 G/s with 40 KiB);
 //   - L2::128B prefetch on the table loads: every miss then costs 4 sectors, no gain;
 //   - cudaLimitMaxL2FetchGranularity = 32: accepted, no effect on the 37 G/s big-table ceiling.
+#include <cstddef>
 #include <cstdlib>
 #include <mutex>
 
@@ -67,7 +68,13 @@ struct ProbeArgs {
   int seg_parts;
   const int *gate;  // optional device-side switch: run only if (*gate != 0) == gate_want
   int gate_want;
+  // payload columns (PAY kernels only): pay[c][i] belongs to the table entry at index i (LP slot / chain position)
+  int n_pay = 0;
+  const int64_t *pay[CC_MAX_PAYLOAD_COLS] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t *out_pay[CC_MAX_PAYLOAD_COLS] = {nullptr, nullptr, nullptr, nullptr};  // result columns, any may be NULL
+  unsigned long long *col_sum = nullptr;  // device array [CC_MAX_PAYLOAD_COLS]: wrapping sums of the payloads of all result rows
 };
+static_assert(CC_MAX_PAYLOAD_COLS == 4, "ProbeArgs initialisers and the unrolled column loops assume 4 payload columns");
 
 // Cache mode HINT (MODE bit 1): L2 eviction priorities (createpolicy + L2::cache_hint) -- the
 // probe keys and the result columns are touched exactly once (evict_first, no L1 allocation),
@@ -195,6 +202,61 @@ __device__ __forceinline__ void emit_matches(const ProbeArgs &a, ProbeShared &sh
   }
 }
 
+// The same compaction step for a table with payload columns: a match at table index idx[j] also emits pay[c][idx[j]].
+// Column by column, the (up to four) gathers of a thread are issued together before their stores.
+template <int MODE>
+__device__ __forceinline__ void emit_matches_pay(const ProbeArgs &a, ProbeShared &sh, const CachePolicy &pol, const bool (&m)[kPbKeysPerThread],
+                                                 const uint64_t (&k)[kPbKeysPerThread], const uint64_t (&v)[kPbKeysPerThread],
+                                                 const uint64_t (&idx)[kPbKeysPerThread], size_t tbase, uint64_t &ksum, uint64_t &psum,
+                                                 uint64_t (&csum)[CC_MAX_PAYLOAD_COLS]) {
+  const unsigned w = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+  unsigned bal[kPbKeysPerThread];
+#pragma unroll
+  for (int j = 0; j < kPbKeysPerThread; ++j) {
+    bal[j] = __ballot_sync(0xffffffffu, m[j]);
+    if (lane_id() == 0) sh.cnt[j * kPbWarps + w] = __popc(bal[j]);
+  }
+  __syncthreads();
+  if (w == 0) {
+    uint32_t c = sh.cnt[lane_id()];
+    uint32_t incl = warp_incl_scan_u32(c);
+    sh.cnt[lane_id()] = incl - c;
+    if (lane_id() == 31) sh.base = incl ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) incl) : 0ull;
+  }
+  __syncthreads();
+  const uint64_t base = sh.base;
+  uint64_t dst[kPbKeysPerThread];
+  bool wr[kPbKeysPerThread];
+#pragma unroll
+  for (int j = 0; j < kPbKeysPerThread; ++j) {
+    dst[j] = base + sh.cnt[j * kPbWarps + w] + __popc(bal[j] & lt);
+    wr[j] = m[j] && dst[j] < a.cap;
+    if (m[j]) {
+      ksum += k[j];
+      psum += v[j];
+    }
+    if (wr[j]) {
+      if (a.out_key) st_stream_u64<MODE>(a.out_key + dst[j], k[j], pol);
+      if (a.out_payload) st_stream_u64<MODE>(a.out_payload + dst[j], v[j], pol);
+      if (a.out_rowid) st_stream_u64<MODE>(a.out_rowid + dst[j], tbase + (size_t) j * kPbThreads + threadIdx.x, pol);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c) {
+    if (c < a.n_pay) {
+      uint64_t t[kPbKeysPerThread];
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) t[j] = m[j] ? ld_table_u64<MODE>((const uint64_t *) a.pay[c] + idx[j], pol) : 0ull;
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) {
+        csum[c] += t[j];
+        if (wr[j] && a.out_pay[c]) st_stream_u64<MODE>(a.out_pay[c] + dst[j], t[j], pol);
+      }
+    }
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePolicy &pol, unsigned long long off, uint32_t rows,
                                                uint64_t (&kn)[kPbKeysPerThread]) {
@@ -205,11 +267,13 @@ __device__ __forceinline__ void load_tile_keys(const ProbeArgs &a, const CachePo
 }
 
 // W32: the table has at most 2^32 slots / buckets, so slot arithmetic runs in 32 bits
-template <int KIND, bool UNIQUE, int MODE, bool W32>
-__global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a) {
+// PAY: the table carries payload columns -- a match also gathers pay[c][table index of the match]
+template <int KIND, bool UNIQUE, int MODE, bool W32, bool PAY = false>
+__global__ void __launch_bounds__(kPbThreads, PAY ? 3 : 4) probe_batch_kernel(ProbeArgs a) {
   __shared__ ProbeShared sh;
   const CachePolicy pol = make_policies();
   uint64_t ksum = 0, psum = 0;
+  uint64_t csum[CC_MAX_PAYLOAD_COLS] = {0, 0, 0, 0};
   if (a.gate && ((*a.gate != 0) != (a.gate_want != 0))) return;  // device-side strategy switch (CTA-uniform)
   // dynamic tile scheduling: one tile is being processed, the keys of the next are in flight, and thread 0
   // fetches the one after that while the CTA works (published through the emit barriers)
@@ -297,7 +361,10 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
         }
       }
       if (threadIdx.x == 0) tile_fetch(a, sh, g_after, sh.off_a, sh.rows_a);
-      emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
+      if (PAY)
+        emit_matches_pay<MODE>(a, sh, pol, m, k, v, pos, tbase, ksum, psum, csum);  // pos[j] = table index of key j's match
+      else
+        emit_matches<MODE>(a, sh, pol, m, k, v, tbase, ksum, psum);
     } else {
       // ---- tables with duplicate keys: a lane keeps walking past its matches (linear_probing_ht.cpp:101-109).
       // One round = up to kRoundEntries Next() steps of every live key at once: the thread loads the next entries of
@@ -309,11 +376,13 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
       bool any;
       do {
         uint32_t mm[kPbKeysPerThread];
+        uint64_t pos0[kPbKeysPerThread];  // PAY: table index the round started at (match bit q <-> entry pos0 + q)
         uint32_t cnt = 0;
         bool mine = false;
 #pragma unroll
         for (int j = 0; j < kPbKeysPerThread; ++j) {
           mm[j] = 0;
+          if (PAY) pos0[j] = pos[j];
           if (act[j]) {
             uint64_t e[kRoundEntries];
             if (KIND == CC_HT_CHAIN) {
@@ -365,11 +434,23 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
           ksum += k[j] * c;
           psum += k[j] * c;  // payload of a match == the matched build key == the probe key
           while (bits) {
+            const uint32_t q = (uint32_t) __ffs((int) bits) - 1u;
             bits &= bits - 1;
             if (dst < a.cap) {
               if (a.out_key) st_stream_u64<MODE>(a.out_key + dst, k[j], pol);
               if (a.out_payload) st_stream_u64<MODE>(a.out_payload + dst, k[j], pol);
               if (a.out_rowid) st_stream_u64<MODE>(a.out_rowid + dst, tbase + (size_t) j * kPbThreads + threadIdx.x, pol);
+            }
+            if (PAY) {
+              const uint64_t at = KIND == CC_HT_LP ? ((pos0[j] + q) & a.mask) : pos0[j] + q;
+#pragma unroll
+              for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c) {
+                if (c < a.n_pay) {
+                  const uint64_t t = ld_table_u64<MODE>((const uint64_t *) a.pay[c] + at, pol);
+                  csum[c] += t;
+                  if (dst < a.cap && a.out_pay[c]) st_stream_u64<MODE>(a.out_pay[c] + dst, t, pol);
+                }
+              }
             }
             ++dst;
           }
@@ -389,6 +470,13 @@ __global__ void __launch_bounds__(kPbThreads, 4) probe_batch_kernel(ProbeArgs a)
   if (lane_id() == 0 && (ksum | psum)) {
     atomicAdd((unsigned long long *) &a.res->key_sum, (unsigned long long) ksum);
     atomicAdd((unsigned long long *) &a.res->payload_sum, (unsigned long long) psum);
+  }
+  if (PAY) {
+#pragma unroll
+    for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c) {
+      const uint64_t t = warp_sum_u64(csum[c]);
+      if (lane_id() == 0 && t && c < a.n_pay) atomicAdd(a.col_sum + c, (unsigned long long) t);
+    }
   }
 }
 
@@ -731,18 +819,18 @@ __global__ void probe_finish_kernel(cc_probe_result *res, size_t cap, const int 
   if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = (res->n_matches > cap ? 1 : 0) | ((region_flag && *region_flag) ? 2 : 0);
 }
 
-template <int KIND, bool UNIQUE, int MODE, bool W32>
+template <int KIND, bool UNIQUE, int MODE, bool W32, bool PAY = false>
 static int launch_probe_w(const ProbeArgs &a, cudaStream_t st) {
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
-    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE, MODE, W32>, kPbThreads, 0));
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_batch_kernel<KIND, UNIQUE, MODE, W32, PAY>, kPbThreads, 0));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
   size_t ntiles = a.seg_parts ? (size_t) a.seg_parts * (size_t) (a.seg_cap / kPbTile) : (a.n + kPbTile - 1) / kPbTile;
   size_t grid = (size_t) sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid == 0) grid = 1;
-  probe_batch_kernel<KIND, UNIQUE, MODE, W32><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
+  probe_batch_kernel<KIND, UNIQUE, MODE, W32, PAY><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -785,6 +873,8 @@ static bool lean_enabled() {
 
 template <int KIND, bool UNIQUE, int MODE>
 static int launch_probe(const ProbeArgs &a, cudaStream_t st) {
+  if (a.n_pay > 0)  // payload columns: the generic kernel knows the table index of every match
+    return a.mask <= 0xFFFFFFFFull ? launch_probe_w<KIND, UNIQUE, MODE, true, true>(a, st) : launch_probe_w<KIND, UNIQUE, MODE, false, true>(a, st);
   if (UNIQUE && lean_enabled() && a.mask <= 0xFFFFFFFFull && !a.out_rowid) return launch_probe_lean<KIND, MODE>(a, st);
   return a.mask <= 0xFFFFFFFFull ? launch_probe_w<KIND, UNIQUE, MODE, true>(a, st) : launch_probe_w<KIND, UNIQUE, MODE, false>(a, st);
 }
@@ -829,10 +919,15 @@ static int log2_floor(size_t x) {
   return l;
 }
 
-static bool want_partitioned(const cc_ht *ht, size_t n, const uint64_t *d_out_rowid) {
+// bytes a probe may touch: keys (+ bucket directory) and, for a probe that gathers payloads, the payload columns
+static size_t probed_table_bytes(const cc_ht *ht, int n_pay) {
+  return ht->kind == CC_HT_LP ? ht->n_slots * 8 * (size_t) (1 + n_pay) : ht->n_slots * 8 + ht->n_keys * 8 * (size_t) (1 + n_pay);
+}
+
+static bool want_partitioned(const cc_ht *ht, size_t n, const uint64_t *d_out_rowid, int n_pay = 0) {
   if (d_out_rowid) return false;  // row ids refer to input order
   if (g_strategy == 1) return false;
-  size_t table_bytes = ht->kind == CC_HT_LP ? ht->n_slots * 8 : ht->n_slots * 8 + ht->n_keys * 8;
+  size_t table_bytes = probed_table_bytes(ht, n_pay);
   if (g_strategy == 2) return table_bytes >= 2 * g_slice_bytes && n > 0;
   // auto: the table must be far beyond L2 AND the batch must revisit each 128-byte table line at
   // least twice on average, otherwise grouping the keys buys no L2 reuse
@@ -849,9 +944,25 @@ static void dense_rows_on_device(ProbeArgs &a, unsigned long long *ctl, size_t n
 }
 
 // seg (optional): the key column is segmented (SegIn, partition.cuh) -- n is then segments * cap, an upper bound of the row count
+// Payload request of a probe: which of the table's payload columns to gather and where to put them
+struct PayIO {
+  int n = 0;
+  int64_t *out[CC_MAX_PAYLOAD_COLS] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long *col_sum = nullptr;
+};
+
 int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
-                       uint64_t *d_out_rowid, size_t cap, cc_probe_result *d_result, cudaStream_t st, SegIn seg = SegIn()) {
+                       uint64_t *d_out_rowid, size_t cap, cc_probe_result *d_result, cudaStream_t st, SegIn seg = SegIn(),
+                       PayIO pay = PayIO()) {
   ProbeArgs a;
+  a.n_pay = pay.n;
+  a.col_sum = pay.col_sum;
+  bool any_pay_out = false;
+  for (int c = 0; c < pay.n; ++c) {
+    a.pay[c] = ht->d_pay[c];
+    a.out_pay[c] = pay.out[c];
+    any_pay_out |= pay.out[c] != nullptr;
+  }
   a.slots = ht->d_slots;
   a.dir = ht->d_dir;
   a.ckeys = ht->d_ckeys;
@@ -861,7 +972,7 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
   a.out_key = d_out_key;
   a.out_payload = d_out_payload;
   a.out_rowid = d_out_rowid;
-  a.cap = (d_out_key || d_out_payload || d_out_rowid) ? cap : 0;
+  a.cap = (d_out_key || d_out_payload || d_out_rowid || any_pay_out) ? cap : 0;
   a.res = d_result;
   a.tile_counter = nullptr;
   a.seg_prefix = nullptr;
@@ -872,8 +983,8 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
   a.gate_want = 0;
   CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
   if (n) {
-    const bool part = want_partitioned(ht, n, d_out_rowid);
-    size_t table_bytes = ht->kind == CC_HT_LP ? ht->n_slots * 8 : ht->n_slots * 8 + ht->n_keys * 8;
+    const bool part = want_partitioned(ht, n, d_out_rowid, pay.n);
+    size_t table_bytes = probed_table_bytes(ht, pay.n);
     int log2_slots = log2_floor(ht->n_slots);
     int log2p = log2_floor((table_bytes + g_slice_bytes - 1) / g_slice_bytes);
     if ((size_t) 1 << log2p < (table_bytes + g_slice_bytes - 1) / g_slice_bytes) ++log2p;
@@ -964,7 +1075,7 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
     cudaFreeAsync(ctl, st);
     CC_TRY(rc);
   }
-  if (a.cap || d_out_key || d_out_payload || d_out_rowid) {
+  if (a.cap || d_out_key || d_out_payload || d_out_rowid || any_pay_out) {
     probe_finish_kernel<<<1, 32, 0, st>>>(d_result, a.cap);
     CC_CHECK_LAUNCH();
   }
@@ -1169,6 +1280,27 @@ int cc_probe_batch_segmented(const cc_ht *ht, const int64_t *d_keys, int n_segme
   seg.segments = n_segments;
   return probe_batch_device(ht, d_keys, (size_t) n_segments * segment_capacity, d_out_key, d_out_payload, nullptr, out_capacity, d_result,
                             as_stream(s), seg);
+}
+
+int cc_probe_batch_payload(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_build_key,
+                           int64_t *const *h_out_payload_cols, size_t n_out_cols, uint64_t *d_out_rowid, size_t out_capacity,
+                           cc_probe_payload_result *d_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(ht && d_result, "NULL argument");
+  CC_REQUIRE(n == 0 || d_keys, "d_keys is NULL");
+  CC_REQUIRE(ht->n_pay > 0, "the table has no payload columns (cc_ht_attach_payload)");
+  CC_REQUIRE(n_out_cols <= (size_t) ht->n_pay, "n_out_cols (%zu) exceeds the table's %d payload columns", n_out_cols, ht->n_pay);
+  CC_REQUIRE(n_out_cols == 0 || h_out_payload_cols, "h_out_payload_cols is NULL");
+  static_assert(offsetof(cc_probe_payload_result, overflow) == offsetof(cc_probe_result, overflow) &&
+                    offsetof(cc_probe_payload_result, col_sum) == sizeof(cc_probe_result),
+                "cc_probe_payload_result must start with a cc_probe_result");
+  PayIO pay;
+  pay.n = ht->n_pay;  // every column is summed; only the requested ones are written
+  for (size_t c = 0; c < n_out_cols; ++c) pay.out[c] = h_out_payload_cols[c];
+  pay.col_sum = reinterpret_cast<unsigned long long *>(d_result->col_sum);
+  CC_CUDA(cudaMemsetAsync(d_result->col_sum, 0, sizeof(d_result->col_sum), as_stream(s)));
+  return probe_batch_device(ht, d_keys, n, d_out_key, d_out_build_key, d_out_rowid, out_capacity, reinterpret_cast<cc_probe_result *>(d_result),
+                            as_stream(s), SegIn(), pay);
 }
 
 int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,

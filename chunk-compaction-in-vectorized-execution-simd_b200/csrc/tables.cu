@@ -282,6 +282,51 @@ __global__ void chain_finalize_kernel(const int64_t *__restrict__ keys, size_t n
   if (local_max) atomicMax(max_chain, (unsigned long long) local_max);
 }
 
+// ------------------------------------------------------------- payload columns
+struct PayCols {
+  const int64_t *src[CC_MAX_PAYLOAD_COLS];
+  int64_t *dst[CC_MAX_PAYLOAD_COLS];
+  int n;
+};
+
+// LP: build row i walks the probe sequence of its key and claims the first slot that holds the key and that no other
+// row has claimed yet (duplicates of a key own as many slots as there are rows with that key, so every row finds one),
+// then drops its payloads at the slot's index.
+__global__ void lp_place_payload_kernel(const int64_t *__restrict__ keys, size_t n, const uint64_t *__restrict__ slots, uint64_t mask,
+                                        uint32_t *claimed, PayCols p, int *flags) {
+  size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = (uint64_t) keys[i];
+    uint64_t s = murmurhash64(k) & mask;
+    bool placed = false;
+    for (uint64_t step = 0; step <= mask; ++step) {
+      const uint64_t cur = slots[s];
+      if (cur == kEmptyU) break;
+      if (cur == k && atomicCAS(claimed + s, 0u, 1u) == 0u) {
+        for (int c = 0; c < p.n; ++c) p.dst[c][s] = p.src[c][i];
+        placed = true;
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+    if (!placed) atomicOr(flags, 1);  // d_build_keys is not the column this table was built from
+  }
+}
+
+// chain: entry at chain position q came from build row rowid[q]
+__global__ void chain_place_payload_kernel(const uint32_t *__restrict__ rowid, size_t n, PayCols p) {
+  size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const uint32_t r = rowid[q];
+    for (int c = 0; c < p.n; ++c) p.dst[c][q] = p.src[c][r];
+  }
+}
+
+__global__ void gen_ref_payload_kernel(int64_t *__restrict__ pay, size_t n) {  // chaining_ht.cpp:21: payload = cnt + 10000000
+  size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) pay[i] = (int64_t) (i + 10000000);
+}
+
 static int launch_grid(size_t n, int threads, int per_sm = 8) {
   size_t blocks = (n + threads - 1) / threads;
   size_t cap = (size_t) sm_count() * per_sm;
@@ -389,6 +434,8 @@ static void free_table(cc_ht *ht) {
   if (ht->d_dir) cudaFree(ht->d_dir);
   if (ht->d_ckeys) cudaFree(ht->d_ckeys);
   if (ht->d_rowid) cudaFree(ht->d_rowid);
+  for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c)
+    if (ht->d_pay[c]) cudaFree(ht->d_pay[c]);
   delete ht;
 }
 
@@ -430,6 +477,126 @@ int cc_ht_build_reference(cc_ht **out, int kind, size_t n, size_t cf, cc_stream_
   cudaStreamSynchronize(as_stream(s));
   cudaFree(d_keys);
   return rc;
+}
+
+int cc_ht_attach_payload(cc_ht *ht, const int64_t *d_build_keys, const int64_t *const *h_payload_cols, size_t n_cols, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(ht, "ht is NULL");
+  CC_REQUIRE(n_cols >= 1 && n_cols <= CC_MAX_PAYLOAD_COLS, "n_cols must be in [1, %d]", CC_MAX_PAYLOAD_COLS);
+  CC_REQUIRE(h_payload_cols, "h_payload_cols is NULL");
+  CC_REQUIRE(ht->kind == CC_HT_CHAIN || d_build_keys || ht->n_keys == 0, "an LP table needs d_build_keys to place the payloads");
+  CC_REQUIRE(ht->kind == CC_HT_LP || ht->d_rowid, "chain table without row ids");
+  for (size_t c = 0; c < n_cols; ++c) CC_REQUIRE(h_payload_cols[c] || ht->n_keys == 0, "payload column %zu is NULL", c);
+  cudaStream_t st = as_stream(s);
+  for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c)
+    if (ht->d_pay[c]) {
+      cudaFree(ht->d_pay[c]);
+      ht->d_pay[c] = nullptr;
+      ht->bytes -= (ht->kind == CC_HT_LP ? ht->n_slots : (ht->n_keys ? ht->n_keys : 1)) * sizeof(int64_t);
+    }
+  ht->n_pay = 0;
+  const size_t rows = ht->kind == CC_HT_LP ? ht->n_slots : (ht->n_keys ? ht->n_keys : 1);
+  PayCols p;
+  p.n = (int) n_cols;
+  for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c) p.src[c] = nullptr, p.dst[c] = nullptr;
+  for (size_t c = 0; c < n_cols; ++c) {
+    cudaError_t e = cudaMalloc(&ht->d_pay[c], rows * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ht->d_pay[c], 0, rows * sizeof(int64_t), st);
+    if (e != cudaSuccess) {
+      set_error("cc_ht_attach_payload: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      for (int d = 0; d < CC_MAX_PAYLOAD_COLS; ++d)
+        if (ht->d_pay[d]) {
+          cudaFree(ht->d_pay[d]);
+          ht->d_pay[d] = nullptr;
+        }
+      return e == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA;
+    }
+    p.src[c] = h_payload_cols[c];
+    p.dst[c] = ht->d_pay[c];
+  }
+  int h_flags = 0;
+  if (ht->n_keys) {
+    const int grid = launch_grid(ht->n_keys, 256, 16);
+    if (ht->kind == CC_HT_LP) {
+      uint32_t *d_claimed = nullptr;
+      int *d_flags = nullptr;
+      CC_CUDA(cudaMalloc(&d_claimed, ht->n_slots * sizeof(uint32_t)));
+      CC_CUDA(cudaMalloc(&d_flags, sizeof(int)));
+      CC_CUDA(cudaMemsetAsync(d_claimed, 0, ht->n_slots * sizeof(uint32_t), st));
+      CC_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), st));
+      lp_place_payload_kernel<<<grid, 256, 0, st>>>(d_build_keys, ht->n_keys, ht->d_slots, ht->mask, d_claimed, p, d_flags);
+      note_launch();
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      cudaFree(d_claimed);
+      cudaFree(d_flags);
+      CC_CUDA(e);
+    } else {
+      chain_place_payload_kernel<<<grid, 256, 0, st>>>(ht->d_rowid, ht->n_keys, p);
+      CC_CHECK_LAUNCH();
+      CC_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  if (h_flags) {
+    for (int c = 0; c < CC_MAX_PAYLOAD_COLS; ++c)
+      if (ht->d_pay[c]) {
+        cudaFree(ht->d_pay[c]);
+        ht->d_pay[c] = nullptr;
+      }
+    set_error("cc_ht_attach_payload: d_build_keys is not the key column this table was built from");
+    return CC_ERR_INVALID;
+  }
+  ht->n_pay = (int) n_cols;
+  ht->bytes += n_cols * rows * sizeof(int64_t);
+  return CC_OK;
+}
+
+int cc_ht_build_reference_payload(cc_ht **out, int kind, size_t n, size_t cf, cc_stream_t s) {
+  CC_REQUIRE(out, "ht is NULL");
+  *out = nullptr;
+  CC_TRY(require_device());
+  CC_REQUIRE(cf > 0, "chunk_factor must be > 0");
+  cudaStream_t st = as_stream(s);
+  int64_t *d_keys = nullptr, *d_pay = nullptr;
+  CC_CUDA(cudaMalloc(&d_keys, (n ? n : 1) * sizeof(int64_t)));
+  cudaError_t e = cudaMalloc(&d_pay, (n ? n : 1) * sizeof(int64_t));
+  if (e != cudaSuccess) {
+    cudaFree(d_keys);
+    CC_CUDA(e);
+  }
+  int rc = cc_gen_build_keys(d_keys, n, cf, s);
+  if (rc == CC_OK && n) {
+    gen_ref_payload_kernel<<<launch_grid(n, 256, 8), 256, 0, st>>>(d_pay, n);
+    note_launch();
+    if (cudaGetLastError() != cudaSuccess) rc = CC_ERR_CUDA;
+  }
+  if (rc == CC_OK) rc = cc_ht_build(out, kind, d_keys, n, CC_BUILD_ORDERED, s);
+  if (rc == CC_OK) {
+    const int64_t *cols[1] = {d_pay};
+    rc = cc_ht_attach_payload(*out, d_keys, cols, 1, s);
+    if (rc != CC_OK) {
+      free_table(*out);
+      *out = nullptr;
+    }
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(d_keys);
+  cudaFree(d_pay);
+  return rc;
+}
+
+size_t cc_ht_payload_cols(const cc_ht *ht) { return ht ? (size_t) ht->n_pay : 0; }
+
+int cc_ht_export_payload(const cc_ht *ht, int64_t *const *h_cols) {
+  CC_REQUIRE(ht && h_cols, "NULL argument");
+  const size_t rows = ht->kind == CC_HT_LP ? ht->n_slots : ht->n_keys;
+  for (int c = 0; c < ht->n_pay; ++c) {
+    CC_REQUIRE(h_cols[c], "h_cols[%d] is NULL", c);
+    if (rows) CC_CUDA(cudaMemcpy(h_cols[c], ht->d_pay[c], rows * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  }
+  return CC_OK;
 }
 
 int cc_ht_import_lp(cc_ht **out, const int64_t *h_slots, size_t n_slots, size_t n_keys, cc_stream_t s) {

@@ -7,7 +7,7 @@
 // in-kernel compaction).  Prints one JSON line: tuple count, per-column sums and the SURVEY 8c digest.
 //
 //   pipeline_main --join-num 4 --chunk-factor 5 --lhs-size 300000 --rhs-size 20000
-//                 [--block 256] [--compact none|full|<threshold>] [--mode chunk|fused] [--table chain|lp]
+//                 [--block 256] [--compact none|full|<threshold>] [--mode chunk|fused|payload] [--table chain|lp]
 #include <chrono>
 #include <cstring>
 #include <random>
@@ -154,10 +154,34 @@ int Run(bool fused, bool compact, size_t threshold) {
   return 0;
 }
 
+// `--mode payload`: ONE join over the first LHS column against a table that keeps the payload the reference
+// generates and drops (chaining_ht.cpp:21-23,34); result rows (probe key, build key, payload) through
+// HT::ProbeBatchPayload.  Reported like the other modes (3 columns).
+template <class HT>
+int RunPayload() {
+  std::mt19937 gen(2);  // main.cpp:41-43, first column only
+  std::uniform_int_distribution<> dist(0, kRHSTupleSize);
+  vector<Attribute> keys(kLHSTupleSize);
+  for (size_t i = 0; i < kLHSTupleSize; ++i) {
+    keys[i] = size_t(dist(gen));
+    for (size_t j = 1; j < kJoins; ++j) (void) dist(gen);  // row-major draw order of the reference
+  }
+  HT ht(kRHSTupleSize, kChunkFactor, /*keep_payload=*/true);
+  auto t0 = std::chrono::steady_clock::now();
+  auto cols = ht.ProbeBatchPayload(keys, kLHSTupleSize * kChunkFactor);
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  const size_t n = cols.empty() ? 0 : cols[0].size();
+  vector<Attribute> rows(n * cols.size());
+  for (size_t c = 0; c < cols.size(); ++c)
+    for (size_t i = 0; i < n; ++i) rows[i * cols.size() + c] = cols[c][i];
+  Report("payload", cols.size(), rows, secs);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
-  bool fused = false, compact = false, lp = false;
+  bool fused = false, compact = false, lp = false, payload = false;
   size_t threshold = 0;
   kBlockSize = 256;
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -167,7 +191,7 @@ int main(int argc, char **argv) {
     else if (a == "--lhs-size") kLHSTupleSize = std::stoi(v);
     else if (a == "--rhs-size") kRHSTupleSize = std::stoi(v);
     else if (a == "--block") kBlockSize = std::stoi(v);
-    else if (a == "--mode") fused = v == "fused";
+    else if (a == "--mode") fused = v == "fused", payload = v == "payload";
     else if (a == "--table") lp = v == "lp";
     else if (a == "--compact") {
       compact = v != "none";
@@ -177,6 +201,7 @@ int main(int argc, char **argv) {
   if (threshold == SIZE_MAX) threshold = fused ? CC_CHAIN_WIDTH : kBlockSize;
   try {
     Check(cc_device_init(0));
+    if (payload) return lp ? RunPayload<LPHashTable>() : RunPayload<HashTable>();
     return lp ? Run<LPHashTable>(fused, compact, threshold) : Run<HashTable>(fused, compact, threshold);
   } catch (const std::exception &e) {
     fprintf(stderr, "pipeline_main: %s\n", e.what());

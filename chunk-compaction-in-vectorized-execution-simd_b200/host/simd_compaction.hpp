@@ -12,6 +12,7 @@
 // Header-only; needs C++17.  Build:  g++ -std=c++17 -Iinclude -I<pkg>/host driver.cpp -L<pkg> -lccb200
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <iostream>
@@ -240,6 +241,48 @@ class BasicHashTable {
  public:
   using Scan = BasicScanStructure<KIND>;
   BasicHashTable(size_t n_rhs_tuples, size_t chunk_factor) { Check(cc_ht_build_reference(&ht_, KIND, n_rhs_tuples, chunk_factor, nullptr)); }
+  // keep_payload: keep the `payload = cnt + 10000000` column the reference generates and drops (chaining_ht.cpp:21-23,34)
+  BasicHashTable(size_t n_rhs_tuples, size_t chunk_factor, bool keep_payload) {
+    Check(keep_payload ? cc_ht_build_reference_payload(&ht_, KIND, n_rhs_tuples, chunk_factor, nullptr)
+                       : cc_ht_build_reference(&ht_, KIND, n_rhs_tuples, chunk_factor, nullptr));
+  }
+  // explicit build tuples (host): keys plus payload columns
+  BasicHashTable(const vector<Attribute> &keys, const vector<vector<Attribute>> &payload_cols) : BasicHashTable(keys) {
+    if (payload_cols.empty()) return;
+    DeviceArray<Attribute> k(keys.size() ? keys.size() : 1, false);
+    k.FromHost(keys.data(), keys.size());
+    vector<std::unique_ptr<DeviceArray<Attribute>>> cols;
+    vector<const int64_t *> ptrs;
+    for (auto &c : payload_cols) {
+      cols.push_back(std::make_unique<DeviceArray<Attribute>>(keys.size() ? keys.size() : 1, false));
+      cols.back()->FromHost(c.data(), std::min(c.size(), keys.size()));
+      ptrs.push_back(cols.back()->data());
+    }
+    Check(cc_ht_attach_payload(ht_, k.data(), ptrs.data(), ptrs.size(), nullptr));
+  }
+  size_t PayloadColumns() const { return cc_ht_payload_cols(ht_); }
+  // Whole-column probe with dense output (cc_probe_batch_payload): returns the result rows
+  // (probe key, matched build key, payload columns...) column-major on the host.
+  vector<vector<Attribute>> ProbeBatchPayload(const vector<Attribute> &probe_keys, size_t capacity) {
+    const size_t ncol = PayloadColumns();
+    DeviceArray<Attribute> k(probe_keys.size() ? probe_keys.size() : 1, false);
+    k.FromHost(probe_keys.data(), probe_keys.size());
+    vector<std::unique_ptr<DeviceArray<Attribute>>> out;
+    vector<int64_t *> ptrs;
+    for (size_t c = 0; c < 2 + ncol; ++c) {
+      out.push_back(std::make_unique<DeviceArray<Attribute>>(capacity ? capacity : 1, false));
+      ptrs.push_back(out.back()->data());
+    }
+    DeviceArray<uint64_t> res(sizeof(cc_probe_payload_result) / sizeof(uint64_t));
+    Check(cc_probe_batch_payload(ht_, k.data(), probe_keys.size(), ptrs[0], ptrs[1], ptrs.data() + 2, ncol, nullptr, capacity,
+                                 reinterpret_cast<cc_probe_payload_result *>(res.data()), nullptr));
+    Check(cc_stream_sync(nullptr));
+    auto r = res.ToHost();
+    const size_t m = std::min<size_t>(r[0], capacity);
+    vector<vector<Attribute>> cols;
+    for (auto &o : out) cols.push_back(o->ToHost(m));
+    return cols;
+  }
   // explicit build keys (host) -- the reference has no external build-input API
   explicit BasicHashTable(const vector<Attribute> &keys) {
     DeviceArray<Attribute> d(keys.size() ? keys.size() : 1, false);

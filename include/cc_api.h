@@ -128,6 +128,29 @@ int cc_ht_export_lp(const cc_ht *ht, int64_t *h_slots);
 int cc_ht_export_chain(const cc_ht *ht, uint32_t *h_begin, uint32_t *h_count, int64_t *h_keys);
 int cc_ht_destroy(cc_ht *ht);
 
+/* ---- real payload columns.  The reference generates `payload = cnt + 10000000` for build row cnt
+ * and then DROPS it: only tuple[0] is pushed into the table (chaining_ht.cpp:21-23,34; linear_probing_ht.cpp:20-22,33),
+ * so a reference result row carries the matched build key twice.  Here a table can keep up to CC_MAX_PAYLOAD_COLS int64
+ * payload columns next to its keys.  Layout: one device array per column, indexed like the keys -- by SLOT for an LP table,
+ * by CHAIN POSITION for a chain table -- so a match found at index i reads its payloads at the same index i and the
+ * partitioned probe keeps key and payload slices in L2 together.  The key layout (and with it every key-only entry
+ * point and its parity) is unchanged.
+ *   d_build_keys : the key column the table was built from (LP: locates the slot of every build row; duplicates of
+ *                  a key are assigned to that key's slots in unspecified order -- every probe of the key returns all
+ *                  of them, so the result multiset does not depend on it); may be NULL for a chain table
+ *   h_payload_cols[n_cols] : HOST array of device column pointers, n_keys rows each
+ * Attaching again replaces the previous payload.                                                                   */
+#define CC_MAX_PAYLOAD_COLS 4
+int cc_ht_attach_payload(cc_ht *ht, const int64_t *d_build_keys, const int64_t *const *h_payload_cols, size_t n_cols,
+                         cc_stream_t stream);
+/* `HashTable(n, cf)` / `LPHashTable(n, cf)` that KEEPS the payload column the reference generates and drops:
+ * payload of build row i = i + 10000000 (chaining_ht.cpp:21)                                                      */
+int cc_ht_build_reference_payload(cc_ht **ht, int kind, size_t n_rhs_tuples, size_t chunk_factor, cc_stream_t stream);
+size_t cc_ht_payload_cols(const cc_ht *ht);
+/* export for tests: h_cols[c] receives column c in table order (LP: n_slots rows, rows of empty slots are 0;
+ * chain: n_keys rows in chain order)                                                                              */
+int cc_ht_export_payload(const cc_ht *ht, int64_t *const *h_cols);
+
 /* ------------------------------------------- chunk-granular probe protocol */
 /* HashTable::Probe (chaining_ht.cpp:38-58) / LPHashTable::Probe
  * (linear_probing_ht.cpp:39-60): d_key_col[block] column storage, d_sel[block]
@@ -198,6 +221,21 @@ int cc_probe_batch(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_
 int cc_probe_batch_segmented(const cc_ht *ht, const int64_t *d_keys, int n_segments, size_t segment_capacity,
                              const uint64_t *d_segment_counts, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity,
                              cc_probe_result *d_result, cc_stream_t stream);
+/* Batch probe of a table with payload columns (cc_ht_attach_payload): result row i is
+ * (d_out_key[i], d_out_build_key[i], h_out_payload_cols[0][i], ...) = probe key, matched build key, payloads of the
+ * matched build row -- the reference result tuple [k, 0, k] with the dropped payload restored.  Any output
+ * pointer may be NULL; h_out_payload_cols is a HOST array of n_out_cols <= cc_ht_payload_cols(ht) device pointers.
+ * Same strategies (direct / partitioned by table slice) and the same dense, unordered output as cc_probe_batch.    */
+typedef struct {
+  uint64_t n_matches;
+  uint64_t key_sum;     /* wrapping sum of probe keys over result rows                    */
+  uint64_t payload_sum; /* wrapping sum of matched build keys over result rows            */
+  uint64_t overflow;
+  uint64_t col_sum[CC_MAX_PAYLOAD_COLS]; /* wrapping sum of every payload column over ALL result rows (also rows cut by overflow) */
+} cc_probe_payload_result;
+int cc_probe_batch_payload(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_build_key,
+                           int64_t *const *h_out_payload_cols, size_t n_out_cols, uint64_t *d_out_rowid, size_t out_capacity,
+                           cc_probe_payload_result *d_result, cc_stream_t stream);
 /* Incremental probe: the key column arrives in pieces (the sub-batches of a multi-GPU exchange) and is probed as ONE batch.
  *   begin : fixes the table, the dense output columns (same contract as cc_probe_batch) and the expected total row count
  *   add   : one piece, dense (n_segments == 0: d_keys[0 .. n)) or segmented (n ignored; layout as in cc_probe_batch_segmented)

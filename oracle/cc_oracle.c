@@ -26,6 +26,81 @@ void orc_murmurhash64_batch(const uint64_t *in, uint64_t *out, size_t n) {
   for (size_t i = 0; i < n; ++i) out[i] = orc_murmurhash64(in[i]);
 }
 
+/* ------------------------------------------------------------------------ */
+/* the join with the payload the reference generates and drops.   */
+void orc_ref_payload(size_t n, int64_t *out) {
+  for (size_t i = 0; i < n; ++i) out[i] = (int64_t)(i + 10000000); /* chaining_ht.cpp:21 */
+}
+
+typedef struct {
+  int64_t *rows;
+  size_t n, cap, width;
+} orc_rowbuf;
+
+static int64_t *rowbuf_next(orc_rowbuf *b) {
+  if (b->n == b->cap) {
+    b->cap = b->cap ? b->cap * 2 : 1024;
+    b->rows = (int64_t *)realloc(b->rows, b->cap * b->width * sizeof(int64_t));
+  }
+  return b->rows + (b->n++) * b->width;
+}
+
+int orc_join_payload(int kind, const int64_t *build_keys, size_t n_build, const int64_t *const *payload_cols, size_t n_cols,
+                     const int64_t *probe_keys, size_t n_probe, int64_t **out_rows, size_t *n_rows) {
+  if (!out_rows || !n_rows || (kind != 0 && kind != 1)) return -1;
+  orc_rowbuf b = {NULL, 0, 0, 2 + n_cols};
+  if (kind == 0) {
+    /* linear_probing_ht.cpp:4-37, with the build row stored beside the key */
+    size_t ns = 1;
+    while (ns < (n_build << 2)) ns <<= 1;
+    const uint64_t mask = ns - 1;
+    int64_t *slots = (int64_t *)malloc(ns * sizeof(int64_t));
+    uint32_t *row = (uint32_t *)malloc(ns * sizeof(uint32_t));
+    for (size_t i = 0; i < ns; ++i) slots[i] = -1;
+    for (size_t i = 0; i < n_build; ++i) {
+      uint64_t s = orc_murmurhash64((uint64_t)build_keys[i]) & mask;
+      while (slots[s] != -1) s = (s + 1) & mask;
+      slots[s] = build_keys[i];
+      row[s] = (uint32_t)i;
+    }
+    /* Probe + Next until the lane retires at an empty slot (linear_probing_ht.cpp:39-115) */
+    for (size_t i = 0; i < n_probe; ++i) {
+      const int64_t k = probe_keys[i];
+      uint64_t s = orc_murmurhash64((uint64_t)k) & mask;
+      while (slots[s] != -1) {
+        if (slots[s] == k) {
+          int64_t *r = rowbuf_next(&b);
+          r[0] = k;
+          r[1] = slots[s];
+          for (size_t c = 0; c < n_cols; ++c) r[2 + c] = payload_cols[c][row[s]];
+        }
+        s = (s + 1) & mask;
+      }
+    }
+    free(slots);
+    free(row);
+  } else {
+    /* chaining_ht.cpp:4-36: node i == build row i, so the node index IS the payload row */
+    orc_chain_table *t = orc_chain_build(build_keys, n_build);
+    const uint64_t mask = t->n_buckets - 1;
+    for (size_t i = 0; i < n_probe; ++i) {
+      const int64_t k = probe_keys[i];
+      for (uint32_t e = t->head[orc_murmurhash64((uint64_t)k) & mask]; e != ORC_NIL; e = t->next[e]) {
+        if (t->key[e] == k) {
+          int64_t *r = rowbuf_next(&b);
+          r[0] = k;
+          r[1] = t->key[e];
+          for (size_t c = 0; c < n_cols; ++c) r[2 + c] = payload_cols[c][e];
+        }
+      }
+    }
+    orc_chain_free(t);
+  }
+  *out_rows = b.rows;
+  *n_rows = b.n;
+  return 0;
+}
+
 void orc_free(void *p) { free(p); }
 
 /* ------------------------------------------------------------------------ */

@@ -179,6 +179,24 @@ uint64_t orc_microbench_lp(const orc_lp_table *t, const int64_t *keys, size_t n,
 uint64_t orc_microbench_chain(const orc_chain_table *t, const int64_t *keys, size_t n, size_t block, int inone,
                               uint64_t *checksum);
 
+/* ---- payload-keeping single join ------------------------------
+ * The reference generates `payload = cnt + 10000000` for build row cnt and pushes
+ * only tuple[0] into its tables (chaining_ht.cpp:21-23,34;
+ * linear_probing_ht.cpp:20-22,33), so its results never carry a payload.  This is
+ * the same build + probe restated with the build ROW kept beside every key: a
+ * match with table entry e yields (probe key, key of e, payload[c][row of e]).
+ * kind 0: LP insertion (linear_probing_ht.cpp:27-36) and the full walk to the first
+ * empty slot (linear_probing_ht.cpp:62-115); kind 1: FIFO chains
+ * (chaining_ht.cpp:28-35) walked to their end (chaining_ht.cpp:60-124).
+ * Parity status of the PAYLOAD VALUES: unpinned by construction -- the reference
+ * cannot produce them; keys, match counts and the row each match comes from follow
+ * the pinned table restatements above, and tests cross-check against an independent
+ * sort-merge join.
+ * out_rows: malloc'ed row-major n_rows x (2 + n_cols) int64 (caller: orc_free).  */
+void orc_ref_payload(size_t n, int64_t *out); /* out[i] = i + 10000000 */
+int orc_join_payload(int kind, const int64_t *build_keys, size_t n_build, const int64_t *const *payload_cols, size_t n_cols,
+                     const int64_t *probe_keys, size_t n_probe, int64_t **out_rows, size_t *n_rows);
+
 /* ---- bandit: negative_feedback.hpp:20-163 (MultiArmedBandit) and
  *      :165-260 (CompactTuner, one bandit per join) ---------------------- */
 typedef struct orc_bandit orc_bandit;

@@ -140,6 +140,9 @@ def lib() -> C.CDLL:
     L.orc_bandit_select.argtypes = [vp]
     L.orc_bandit_update.argtypes = [vp, sz, C.c_double]
     L.orc_bandit_state.argtypes = [vp, vp, vp]
+    L.orc_ref_payload.argtypes = [sz, vp]
+    L.orc_join_payload.restype = C.c_int
+    L.orc_join_payload.argtypes = [C.c_int, vp, sz, C.POINTER(vp), sz, vp, sz, C.POINTER(i64p), C.POINTER(sz)]
     L.orc_free.argtypes = [vp]
     _lib = L
     return L
@@ -273,6 +276,37 @@ def multiplicity_oracle(build_key_arrays, lhs: np.ndarray) -> dict:
     st = ResultStats()
     assert lib().orc_multiplicity_oracle(J, kp, ns, _p(lhs), rows, C.byref(st)) == 0
     return stats_dict(st, J)
+
+
+def ref_payload(n: int) -> np.ndarray:
+    """payload the reference generates and drops: row i -> i + 10000000 (chaining_ht.cpp:21)"""
+    out = np.empty(n, dtype=np.int64)
+    lib().orc_ref_payload(n, _p(out))
+    return out
+
+
+def join_payload(kind: int, build_keys: np.ndarray, payload_cols, probe_keys: np.ndarray) -> np.ndarray:
+    """orc_join_payload: rows (probe key, build key, payload...) of the single join that keeps the build row."""
+    bk = np.ascontiguousarray(build_keys, dtype=np.int64)
+    pk = np.ascontiguousarray(probe_keys, dtype=np.int64)
+    cols = [np.ascontiguousarray(c, dtype=np.int64) for c in payload_cols]
+    assert all(c.size == bk.size for c in cols)
+    cp = (C.c_void_p * max(len(cols), 1))(*[_p(c) for c in cols])
+    out = C.POINTER(C.c_int64)()
+    n = C.c_size_t(0)
+    assert lib().orc_join_payload(kind, _p(bk), bk.size, cp, len(cols), _p(pk), pk.size, C.byref(out), C.byref(n)) == 0
+    w = 2 + len(cols)
+    rows = np.ctypeslib.as_array(out, shape=(n.value, w)).copy() if n.value else np.empty((0, w), dtype=np.int64)
+    lib().orc_free(out)
+    return rows
+
+
+def sort_rows(rows: np.ndarray) -> np.ndarray:
+    """rows in lexicographic order (multiset comparison)"""
+    rows = np.ascontiguousarray(rows)
+    if rows.shape[0] == 0:
+        return rows
+    return rows[np.lexsort(rows.T[::-1])]
 
 
 def digest_tuples(tuples: np.ndarray):

@@ -37,3 +37,19 @@ def test_cpp_driver_matches_reference(ccb, J, cf, lhs, rhs):
     for v in variants:
         r = run(*base, *v)
         assert (r["n_tuples"], r["digest"], r["colsum"]) == (g["n_tuples"], g["digest"], g["colsum"]), (v, r)
+
+
+@pytest.mark.parametrize("table", ["chain", "lp"])
+def test_cpp_driver_payload_mode(ccb, table):
+    """facade HashTable(n, cf, keep_payload) + ProbeBatchPayload vs the payload oracle"""
+    import numpy as np
+
+    import oracle_lib as O
+
+    J, cf, lhs, rhs = 2, 4, 30000, 3000
+    r = run("--join-num", J, "--chunk-factor", cf, "--lhs-size", lhs, "--rhs-size", rhs, "--mode", "payload", "--table", table)
+    keys = O.gen_lhs_main(lhs, J, rhs)[:, 0]
+    want = O.join_payload(0 if table == "lp" else 1, O.build_keys(rhs, cf), [O.ref_payload(rhs)], keys)
+    digest, colsum = O.digest_tuples(want)
+    assert (r["n_tuples"], r["colsum"]) == (want.shape[0], colsum)
+    assert r["digest"] == digest  # the digest is a sum over rows, so row order does not matter

@@ -178,3 +178,31 @@ def test_live_reference_agrees():
         assert d[key] == r[key]
     r2 = O.ref_driver("main", 3, 4, 40000, 3000, 256, 1)
     assert (r2["n_tuples"], r2["digest"]) == (r["n_tuples"], r["digest"])
+
+
+# ------------------------------------------------------------------ payload-keeping join
+def test_payload_join_oracle_against_independent_join():
+    """orc_join_payload (both table kinds) == a numpy sort-merge join; the reference payload is row + 10000000."""
+    assert np.array_equal(O.ref_payload(5), np.arange(5) + 10000000)
+    rng = np.random.Generator(np.random.PCG64(3))
+    for n, cf in [(1000, 1), (4096, 4), (777, 20), (1, 1), (0, 1)]:
+        bk = O.build_keys(n, cf)
+        pay = [O.ref_payload(n), rng.integers(-(1 << 62), 1 << 62, size=n, dtype=np.int64)]
+        keys = rng.integers(0, max(1, 2 * n), size=20000, dtype=np.int64)
+        order = np.argsort(bk, kind="stable")
+        sk = bk[order]
+        lo, hi = np.searchsorted(sk, keys, "left"), np.searchsorted(sk, keys, "right")
+        reps = hi - lo
+        pi = np.repeat(np.arange(keys.size), reps)
+        bi = order[np.concatenate([np.arange(a, b) for a, b in zip(lo[reps > 0], hi[reps > 0])])] if reps.sum() else np.empty(0, dtype=np.int64)
+        want = O.sort_rows(np.stack([keys[pi], bk[bi], pay[0][bi], pay[1][bi]], axis=1))
+        for kind in (0, 1):
+            got = O.join_payload(kind, bk, pay, keys)
+            assert np.array_equal(O.sort_rows(got), want)
+            # key columns agree with the pinned key-only pipeline: same count, same key sums
+            if n:
+                tab = (O.OracleLP if kind == 0 else O.OracleChain)(bk)
+                ref = O.pipeline([tab], keys.reshape(-1, 1), 2048)
+                assert ref["n_tuples"] == got.shape[0]
+                assert ref["colsum"][0] == int(got[:, 0].view(np.uint64).sum(dtype=np.uint64))
+                assert ref["colsum"][2] == int(got[:, 1].view(np.uint64).sum(dtype=np.uint64))
