@@ -14,7 +14,9 @@
 // contiguous range per partition (global atomicAdd), sorts the tile by partition in shared
 // memory and writes it out so that consecutive threads store to consecutive addresses of the
 // same partition (coalesced runs instead of 8-byte scatters).
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "partition.cuh"
@@ -98,8 +100,11 @@ struct ScatterDst {
 // TMA == true: the NEXT tile of keys is pulled into shared memory by one cp.async.bulk (UBLKCP) while the
 // CTA ranks / sorts / stores the current one, so the key stream never waits behind the tile's barriers.
 // (Unlike the probe kernel this kernel does no gathers, so the larger shared-memory carve-out costs nothing.)
+#ifndef CCB_SCATTER_ABLATE
+#define CCB_SCATTER_ABLATE 0
+#endif
 template <bool PEERS, bool TMA>
-__global__ void __launch_bounds__(kPartThreads)
+__global__ void __launch_bounds__(kPartThreads, 2)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
                              unsigned long long *cursors, ScatterDst dst, unsigned long long cap_rows, int *flag, int gated, SegIn seg) {
   // cap_rows > 0 (single-pass mode): partition p owns the fixed region [p * cap_rows, (p + 1) * cap_rows) of the output, no
@@ -109,7 +114,6 @@ __global__ void __launch_bounds__(kPartThreads)
   extern __shared__ __align__(128) unsigned char s_dyn[];
   uint64_t *s_sorted = reinterpret_cast<uint64_t *>(s_dyn);                  // [kPartTile]
   uint64_t *s_in = s_sorted + kPartTile;                                       // [kPartTile] (TMA only)
-  uint16_t *s_part = reinterpret_cast<uint16_t *>(s_dyn + (TMA ? 2 : 1) * kPartTile * sizeof(uint64_t));  // [kPartTile]
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_cnt[kMaxParts];
   __shared__ uint16_t s_off[kMaxParts];  // offsets inside the tile (< kPartTile)
@@ -130,21 +134,17 @@ __global__ void __launch_bounds__(kPartThreads)
       tma_load_1d(s_in, keys + (size_t) blockIdx.x * kPartTile, kPartTile * 8, &s_bar);
     }
   }
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // One tile.  FULL (compile-time): the tile holds kPartTile keys -- all but the ragged last tile of a column and the partly
+  // filled tiles of a segmented one -- so no per-key bounds checks, no sentinel partition ids and a fixed-trip output loop
+  // (halves the instructions per tile: 960 -> 520 per thread).
+  // ABL (CCB_SCATTER_ABLATE, measurement builds only -- results are then WRONG): 1 = no output stores, 2 = no global range
+  // reservation, 3 = no shared-memory ranking atomics, 4 = no sort through shared memory.
+  auto do_tile = [&](auto full_tag, const size_t tile, const uint32_t tile_n) {
+    constexpr bool FULL = decltype(full_tag)::value;
     const size_t tbase = tile * (size_t) kPartTile;
-    const uint32_t tile_n = tile_rows(tile, n, seg);  // CTA-uniform
-    const bool staged = TMA && tile_n == (uint32_t) kPartTile;
+    const bool staged = TMA && FULL;
     const size_t next = tile + gridDim.x;
     const bool next_staged = TMA && next < ntiles && tile_rows(next, n, seg) == (uint32_t) kPartTile;
-    if (tile_n == 0) {
-      // slack tile of a segmented input: nothing to scatter.  No bulk copy is in flight (only complete tiles are staged) and
-      // the previous iteration ended behind a barrier with every read of the staging buffer fenced, so it can be refilled.
-      if (next_staged && threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, kPartTile * 8);
-        tma_load_1d(s_in, keys + next * (size_t) kPartTile, kPartTile * 8, &s_bar);
-      }
-      continue;
-    }
     for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
     uint64_t k[kPartItems];
     uint32_t p[kPartItems], r[kPartItems];
@@ -156,14 +156,25 @@ __global__ void __launch_bounds__(kPartThreads)
     } else {
       const int64_t *src = keys + tbase + threadIdx.x;
 #pragma unroll
-      for (int j = 0; j < kPartItems; ++j) k[j] = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n ? (uint64_t) __ldg(src + j * kPartThreads) : 0;
+      for (int j = 0; j < kPartItems; ++j)
+        k[j] = (FULL || (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n) ? (uint64_t) __ldg(src + j * kPartThreads) : 0;
     }
     __syncthreads();  // s_cnt is cleared (loop top)
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
-      bool ok = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n;
-      p[j] = ok ? fn(k[j]) : 0xFFFFFFFFu;
-      r[j] = ok ? atomicAdd(&s_cnt[p[j]], 1u) : 0;
+      if (FULL) {
+        p[j] = fn(k[j]);
+#if CCB_SCATTER_ABLATE == 3
+        r[j] = (uint32_t) j;
+        if (j == 0 && threadIdx.x < (unsigned) parts) s_cnt[threadIdx.x] = kPartTile / parts;
+#else
+        r[j] = atomicAdd(&s_cnt[p[j]], 1u);
+#endif
+      } else {
+        bool ok = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n;
+        p[j] = ok ? fn(k[j]) : 0xFFFFFFFFu;
+        r[j] = ok ? atomicAdd(&s_cnt[p[j]], 1u) : 0;
+      }
     }
     // Every thread has now CONSUMED its keys (hashed them), so its reads of the staging buffer are complete.
     // The refill is an async-proxy write: it must be ordered after these generic-proxy reads with a proxy fence
@@ -202,7 +213,11 @@ __global__ void __launch_bounds__(kPartThreads)
         if (i < parts) {
           s_off[i] = (uint16_t) run;
           if (c[q]) {
+#if CCB_SCATTER_ABLATE == 2
+            unsigned long long at = (unsigned long long) (tile / gridDim.x) * 24ull;
+#else
             unsigned long long at = atomicAdd(cursors + i, (unsigned long long) c[q]);
+#endif
             if (cap_rows) {
               if (at + c[q] > cap_rows) {
                 atomicOr(flag, 1);
@@ -219,12 +234,16 @@ __global__ void __launch_bounds__(kPartThreads)
       }
     }
     __syncthreads();
+    // the partition id of a sorted key is RE-HASHED in the output loop instead of being parked beside it in shared memory
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j)
-      if (p[j] != 0xFFFFFFFFu) {
+      if (FULL || p[j] != 0xFFFFFFFFu) {
+#if CCB_SCATTER_ABLATE == 4
+        uint32_t slot = (uint32_t) (j * kPartThreads) + threadIdx.x;
+#else
         uint32_t slot = s_off[p[j]] + r[j];
+#endif
         s_sorted[slot] = k[j];
-        s_part[slot] = (uint16_t) p[j];
       }
 #pragma unroll
     for (int q = 0; q < kBins; ++q) {
@@ -232,13 +251,46 @@ __global__ void __launch_bounds__(kPartThreads)
       if (i < parts) s_delta[i] = gbase[q] == ~0ull ? kDroppedRun : gbase[q] - first[q];
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
-      uint32_t pp = s_part[i];
-      int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
-      unsigned long long d = s_delta[pp];
-      if (d != kDroppedRun) out[d + i] = (int64_t) s_sorted[i];
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < kPartItems; ++j) {
+        const uint32_t i = (uint32_t) (j * kPartThreads) + threadIdx.x;
+        const uint64_t key = s_sorted[i];
+        const uint32_t pp = fn(key);
+        int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
+        const unsigned long long d = s_delta[pp];
+#if CCB_SCATTER_ABLATE == 1
+        if (d == kDroppedRun + 12345 + key) out[d + i] = (int64_t) key;
+#else
+        if (d != kDroppedRun) out[d + i] = (int64_t) key;
+#endif
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
+        const uint64_t key = s_sorted[i];
+        const uint32_t pp = fn(key);
+        int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
+        unsigned long long d = s_delta[pp];
+        if (d != kDroppedRun) out[d + i] = (int64_t) key;
+      }
     }
     __syncthreads();
+  };
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t tile_n = tile_rows(tile, n, seg);  // CTA-uniform
+    if (tile_n == (uint32_t) kPartTile) {
+      do_tile(std::true_type(), tile, tile_n);
+    } else if (tile_n == 0) {
+      // slack tile of a segmented input: nothing to scatter.  No bulk copy is in flight (only complete tiles are staged) and
+      // the previous iteration ended behind a barrier with every read of the staging buffer fenced, so it can be refilled.
+      const size_t next = tile + gridDim.x;
+      if (TMA && next < ntiles && tile_rows(next, n, seg) == (uint32_t) kPartTile && threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, kPartTile * 8);
+        tma_load_1d(s_in, keys + next * (size_t) kPartTile, kPartTile * 8, &s_bar);
+      }
+    } else {
+      do_tile(std::false_type(), tile, tile_n);
+    }
   }
 }
 
@@ -246,8 +298,12 @@ template <bool PEERS>
 static int launch_scatter(const int64_t *d_keys, size_t n, PartFn fn, const unsigned long long *d_offsets, unsigned long long *d_cursors,
                           const ScatterDst &dst, size_t blocks, cudaStream_t st, unsigned long long cap_rows = 0, int *flag = nullptr,
                           int gated = 0, SegIn seg = SegIn()) {
-  const bool tma = (reinterpret_cast<uintptr_t>(d_keys) & 15) == 0;  // bulk copies need 16-byte alignment
-  const size_t smem = (tma ? 2 : 1) * (size_t) kPartTile * sizeof(uint64_t) + (size_t) kPartTile * sizeof(uint16_t);
+  static const bool no_tma = [] {  // experiment knob
+    const char *e = getenv("CCB_SCATTER_NO_TMA");
+    return e && e[0] == '1';
+  }();
+  const bool tma = !no_tma && (reinterpret_cast<uintptr_t>(d_keys) & 15) == 0;  // bulk copies need 16-byte alignment
+  const size_t smem = (tma ? 2 : 1) * (size_t) kPartTile * sizeof(uint64_t);
   if (tma) {
     CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated, seg);
