@@ -227,9 +227,14 @@ def main() -> int:
     torch.cuda.set_device(local_rank)
     pkg = importlib.import_module(PKG_NAME)
     pkg.init(local_rank)
+    saved_stdout = None
     if distributed:
         import torch.distributed as dist
 
+        # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr until then
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_build, n_probe = 1 << args.log2_build, 1 << args.log2_probe
     peak, peak_src = measured_peak()
@@ -393,9 +398,14 @@ def main() -> int:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "runs")}
         except Exception as e:  # the baseline is informative; never lose the GPU number over it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if distributed:
+        os.dup2(2, 1)  # teardown chatter, if any, also goes to stderr
         dist.barrier()
         dist.destroy_process_group()
     return 0
