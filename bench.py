@@ -181,6 +181,7 @@ def workload_config(args) -> dict:
                         f"exchange of both sides ({EXCHANGES[args.exchange]}), "
                         f"dense key+payload output (results stay sharded)",
             "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "exchange": args.exchange, "sub_batches": args.sub_batches,
+            "ce_probe": (args.ce_probe if args.ce_probe != "auto" else ("stream" if args.gpus <= 2 else "batch")) if args.exchange == "ce" else None,
             "l2_policy": "inputs far exceed L2; no flush needed"}
 
 
@@ -201,6 +202,9 @@ def main() -> int:
     ap.add_argument("--sub-batches", type=int, default=None,
                     help="N>1: the exchange of sub-batch b+1 overlaps the probe of sub-batch b (default 4 with --exchange ce, else 1)")
     ap.add_argument("--peer-blocks", type=int, default=0, help="N>1 with p2p: CTA cap of the NVLink-bound peer scatter (0 = all SMs)")
+    ap.add_argument("--ce-probe", default="auto", choices=["auto", "stream", "batch"],
+                    help="N>1 with --exchange ce: one incremental probe per step (stream), a probe per landed sub-batch (batch), "
+                         "or stream up to 2 GPUs and batch beyond (auto)")
     ap.add_argument("--exchange", default="ce", choices=["ce", "p2p", "nccl"],
                     help="N>1: copy-engine block copies under the probe (default), fused peer-memory scatter kernel, or NCCL all-to-all")
     args = ap.parse_args()
@@ -252,7 +256,7 @@ def main() -> int:
         local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
         cap_rows = -(-n_probe // args.sub_batches) if args.exchange == "ce" else int(n_probe * 1.05) + (1 << 20)
         join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
-                                   capacity_rows=cap_rows, peer_blocks=args.peer_blocks)
+                                   capacity_rows=cap_rows, peer_blocks=args.peer_blocks, ce_probe=args.ce_probe)
         table = join.table
         del local_build
     torch.cuda.synchronize()

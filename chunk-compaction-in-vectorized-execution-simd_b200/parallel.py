@@ -262,18 +262,25 @@ class PartitionedJoin:
     """Build once, probe many times.  `pkg` is the product package (passed in to avoid a circular import)."""
 
     def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition",
-                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0):
+                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0, ce_probe: str = "auto"):
         """plan: "partition" (hash-partition both sides) or "broadcast" (replicate the build side).
         exchange: "nccl" (scatter locally, then all_to_all_single), "p2p" (PeerExchange: the scatter kernel
         writes into the owners' buffers over NVLink) or "ce" (CopyExchange: single-pass partition + copy-engine block
         copies, overlapped with the probe by probe_pipelined; the build side then travels by all_to_all_single);
-        capacity_rows sizes the p2p receive buffers / the largest "ce" sub-batch."""
+        capacity_rows sizes the p2p receive buffers / the largest "ce" sub-batch.
+        ce_probe: how the "ce" pipeline probes -- "stream": ONE incremental probe per call (the table is streamed from HBM
+        once; best while the NVLink copies hide under the partition kernels, i.e. few GPUs), "batch": every sub-batch is
+        probed as soon as it has landed (the table is streamed once per sub-batch, but the probes run underneath the copy
+        chain, which is what bounds a step on many GPUs), "auto": stream up to 2 GPUs, batch beyond."""
+        if ce_probe not in ("auto", "stream", "batch"):
+            raise ValueError(f"ce_probe must be auto, stream or batch, not {ce_probe!r}")
         self.pkg = pkg
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.log2p = log2_exact(self.world)
         self.plan = plan
+        self.ce_probe = ce_probe if ce_probe != "auto" else ("stream" if self.world <= 2 else "batch")
         self.peer = PeerExchange(pkg, capacity_rows, group, peer_blocks=peer_blocks) if (exchange == "p2p" and plan == "partition") else None
         self.copier = CopyExchange(pkg, capacity_rows, group) if (exchange == "ce" and plan == "partition") else None
         T = pkg.LPHashTable if kind == pkg.CC_HT_LP else pkg.HashTable
@@ -341,11 +348,24 @@ class PartitionedJoin:
         of the received sub-batch into the table-slice regions of ONE incremental probe, cc_probe_stream_*) while the block
         copies C(b) run on the copy stream underneath S(b - 1) / P(b + 1).  The table is streamed once per call, not once per
         sub-batch.  Only results[0] is written (one dense output over all of out_key / out_payload).
+        (ce_probe == "batch" instead probes every sub-batch on arrival, see __init__.)
         Buffer safety with 3 rotating buffers: P(k + 3) is enqueued behind B(k + 1), which completes only when every rank has
         entered it, i.e. after its S(k)."""
         import os
         cx = self.copier
         chunks = list(local_probe_keys.chunk(n_sub))
+        if self.ce_probe == "batch":
+            # P(0) P(1) B(0) L(0) P(2) B(1) L(1) ...  with L = slice partition + probe of ONE received sub-batch: the block
+            # copies C(b + 1) run underneath L(b).  results[b] / slice b of the output columns belong to sub-batch b.
+            cap = out_key.numel() // n_sub
+            pending = [cx.start(chunks[0])]
+            for b in range(len(chunks)):
+                if b + 1 < len(chunks):
+                    pending.append(cx.start(chunks[b + 1]))
+                recv, seg_cap, counts = cx.finish(pending[b])
+                self.table.probe_batch_segmented(recv, self.world, seg_cap, counts, capacity=cap, out_key=out_key[b * cap:(b + 1) * cap],
+                                                 out_payload=out_payload[b * cap:(b + 1) * cap], result=results[b], sync=False)
+            return
         trace = [] if os.environ.get("CCB_CE_TRACE") else None  # evidence switch: CUDA-event timeline of one call (synchronises)
 
         def mark(name):

@@ -178,3 +178,21 @@ def test_partition_single_regions(ccb):
     same = torch.full((n,), 42, dtype=torch.int64, device="cuda")  # every key in one partition: the region must overrun
     _, _, flag = ccb.partition_single(same, log2p, cap)
     assert int(flag.item()) != 0
+
+
+@pytest.mark.parametrize("log2p", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("n", [4096 * 37, 4096 * 600 + 17, 1000])
+def test_partition_single_fanouts(ccb, log2p, n):
+    """Few partitions (<= 16: the multi-GPU owner partition) take the ballot-ranked path of the scatter kernel for full tiles,
+    more take the shared-memory-atomic path; either way every region must hold exactly its partition's keys."""
+    P = 1 << log2p
+    for keys in (ccb.gen_keys_counter(n, 11, (1 << 44) - 1), torch.arange(n, dtype=torch.int64, device="cuda")):
+        cap = ((n // P) * 5 // 4 + 8192 + 4095) // 4096 * 4096
+        out, counts, flag = ccb.partition_single(keys, log2p, cap)
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 0 and int(counts.sum().item()) == n
+        pid = (ccb.murmurhash64(keys).view(torch.int64) >> (64 - log2p)) & (P - 1)
+        for p in range(P):
+            c = int(counts[p].item())
+            assert c == int((pid == p).sum().item())
+            assert torch.equal(torch.sort(out[p * cap: p * cap + c])[0], torch.sort(keys[pid == p])[0])
