@@ -274,12 +274,13 @@ def main() -> int:
     recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if (distributed and args.exchange == "nccl") else None
     expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
 
-    def step():
+    def step(k=None):
+        k = keys if k is None else k
         if not distributed:
-            return table.probe_batch(keys, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
+            return table.probe_batch(k, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
         if args.exchange in ("p2p", "ce"):
-            return join.probe_pipelined(keys, n_sub, out_key, out_payload, result)
-        shuffled = join.shuffle(keys, out=recv_buf)
+            return join.probe_pipelined(k, n_sub, out_key, out_payload, result)
+        shuffled = join.shuffle(k, out=recv_buf)
         return table.probe_batch(shuffled, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
 
     def barrier():
@@ -393,8 +394,51 @@ def main() -> int:
         line["e2e"] = {"value": ne / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8, "d2h_bytes_per_step": ne * 16,
                        "sample": f"2^{ne.bit_length() - 1} probe keys per call through cc_probe_batch_host (pinned host buffers, same table)",
                        "ms_per_step": 1e3 * e2e_s}
-    elif distributed:
+    elif distributed and args.no_e2e:
         line["e2e"] = None
+    elif distributed:
+        # every rank: its probe keys come from pinned host memory, the rows it ends up owning go back to pinned host memory
+        result.zero_()
+        ne = 1 << min(args.e2e_log2_probe - 1, args.log2_probe)
+        hk = torch.empty(ne, dtype=torch.int64, pin_memory=True)
+        hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345 + rank * ne))
+        in_sum = int(hk.sum().item())
+        dk = torch.empty(ne, dtype=torch.int64, device=dev)
+        hok = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+        hop = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+        capb = cap // n_sub  # output slice of one sub-batch (p2p, ce/batch); ce/stream and nccl write one dense run from row 0
+
+        def e2e_step():
+            dk.copy_(hk, non_blocking=True)
+            step(dk)
+            counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
+            off = 0
+            for b, m in enumerate(counts):
+                if m:
+                    hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
+                    hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
+                off += m
+            torch.cuda.synchronize()
+            return off
+
+        e2e_step()
+        ts, rows = [], 0
+        for _ in range(max(3, args.steps)):
+            barrier()
+            t0 = time.perf_counter()
+            rows = e2e_step()
+            ts.append(time.perf_counter() - t0)
+        t = torch.tensor(ts, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
+        chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
+        dist.all_reduce(chk)
+        assert int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0, ("e2e check failed", chk.tolist())
+        e2e_s = float(t.mean().item())
+        line["e2e"] = {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
+                       "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of the "
+                                 f"rows each rank owns into pinned host memory (row counts read back first)",
+                       "ms_per_step": 1e3 * e2e_s}
+        del hk, hok, hop, dk
 
     if rank == 0 and not args.no_cpu_baseline and not distributed:
         try:
