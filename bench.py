@@ -397,47 +397,65 @@ def main() -> int:
     elif distributed and args.no_e2e:
         line["e2e"] = None
     elif distributed:
-        # every rank: its probe keys come from pinned host memory, the rows it ends up owning go back to pinned host memory
+        # every rank: its probe keys come from pinned host memory, the rows it ends up owning go back to pinned host memory.
+        # The buffers are allocated first and the ranks agree on whether all of them succeeded, so that no rank can enter
+        # the collectives of the timed loop alone; a failed check reports e2e = null instead of losing the whole line.
         result.zero_()
         ne = 1 << min(args.e2e_log2_probe - 1, args.log2_probe)
-        hk = torch.empty(ne, dtype=torch.int64, pin_memory=True)
-        hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345 + rank * ne))
-        in_sum = int(hk.sum().item())
-        dk = torch.empty(ne, dtype=torch.int64, device=dev)
-        hok = torch.empty(cap, dtype=torch.int64, pin_memory=True)
-        hop = torch.empty(cap, dtype=torch.int64, pin_memory=True)
-        capb = cap // n_sub  # output slice of one sub-batch (p2p, ce/batch); ce/stream and nccl write one dense run from row 0
+        hk = hok = hop = dk = None
+        try:
+            hk = torch.empty(ne, dtype=torch.int64, pin_memory=True)
+            hok = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+            hop = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+            dk = torch.empty(ne, dtype=torch.int64, device=dev)
+            ready = 1
+        except Exception:
+            ready = 0
+        flag = torch.tensor([ready], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            line["e2e"] = None
+            line["e2e_note"] = "pinned host buffers could not be allocated on every rank"
+        else:
+            hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345 + rank * ne))
+            in_sum = int(hk.sum().item())
+            capb = cap // n_sub  # output slice of one sub-batch (p2p, ce/batch); ce/stream and nccl write one dense run from row 0
+            dense = n_sub == 1 or (args.exchange == "ce" and join.ce_probe == "stream")
 
-        def e2e_step():
-            dk.copy_(hk, non_blocking=True)
-            step(dk)
-            counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
-            off = 0
-            for b, m in enumerate(counts):
-                if m:
-                    hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
-                    hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
-                off += m
-            torch.cuda.synchronize()
-            return off
+            def e2e_step():
+                dk.copy_(hk, non_blocking=True)
+                step(dk)
+                counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
+                off = 0
+                for b, m in enumerate(counts):
+                    m = min(m, cap if dense else capb)
+                    if m:
+                        hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
+                        hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
+                    off += m
+                torch.cuda.synchronize()
+                return off
 
-        e2e_step()
-        ts, rows = [], 0
-        for _ in range(max(3, args.steps)):
-            barrier()
-            t0 = time.perf_counter()
-            rows = e2e_step()
-            ts.append(time.perf_counter() - t0)
-        t = torch.tensor(ts, dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
-        chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
-        dist.all_reduce(chk)
-        assert int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0, ("e2e check failed", chk.tolist())
-        e2e_s = float(t.mean().item())
-        line["e2e"] = {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
-                       "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of the "
-                                 f"rows each rank owns into pinned host memory (row counts read back first)",
-                       "ms_per_step": 1e3 * e2e_s}
+            e2e_step()
+            ts, rows = [], 0
+            for _ in range(max(3, args.steps)):
+                barrier()
+                t0 = time.perf_counter()
+                rows = e2e_step()
+                ts.append(time.perf_counter() - t0)
+            t = torch.tensor(ts, dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
+            chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
+            dist.all_reduce(chk)
+            e2e_s = float(t.mean().item())
+            if int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0:
+                line["e2e"] = {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
+                               "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of "
+                                         f"the rows each rank owns into pinned host memory (row counts read back first)",
+                               "ms_per_step": 1e3 * e2e_s}
+            else:
+                line["e2e"] = None
+                line["e2e_note"] = f"end-to-end check failed (rows, key sum out, key sum in, key != payload): {chk.tolist()}"
         del hk, hok, hop, dk
 
     if rank == 0 and not args.no_cpu_baseline and not distributed:
