@@ -405,8 +405,9 @@ def main() -> int:
         hk = hok = hop = dk = None
         try:
             hk = torch.empty(ne, dtype=torch.int64, pin_memory=True)
-            hok = torch.empty(cap, dtype=torch.int64, pin_memory=True)
-            hop = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+            hcap = ne + ne // 8 + (1 << 16)  # rows this rank can end up owning (hash partition: ne +- a fraction of a percent)
+            hok = torch.empty(hcap, dtype=torch.int64, pin_memory=True)
+            hop = torch.empty(hcap, dtype=torch.int64, pin_memory=True)
             dk = torch.empty(ne, dtype=torch.int64, device=dev)
             ready = 1
         except Exception:
@@ -428,7 +429,7 @@ def main() -> int:
                 counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
                 off = 0
                 for b, m in enumerate(counts):
-                    m = min(m, cap if dense else capb)
+                    m = min(m, cap if dense else capb, hcap - off)
                     if m:
                         hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
                         hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
