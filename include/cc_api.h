@@ -255,7 +255,7 @@ int cc_probe_stream_finish(cc_probe_stream *h, cc_stream_t stream);
  *     batch holds >= max(4 Mi, table_bytes / 64) keys (each 128-byte table line is revisited)
  *     and no row ids are requested; 1 always direct; 2 always partitioned; 3 always partitioned with the
  *     two-pass (histogram + scatter) partition instead of the default single-pass one.
- * slice_bytes: target table bytes per partition (0 keeps the current value, default 16 MiB).
+ * slice_bytes: target table bytes per partition (0 keeps the current value, default 32 MiB).
  * The partitioned path needs n * 8 bytes of stream-ordered scratch (cudaMallocAsync).       */
 int cc_probe_set_strategy(int strategy, size_t slice_bytes);
 /* Cache behaviour of the probe kernel's memory operations (tuning knob; results never change):
