@@ -155,7 +155,8 @@ class CopyExchange:
     starts sub-batch b + 1 before it finishes sub-batch b: the copies of b + 1 run underneath the probe of b, and per key the
     SMs only do the owner partition, the slice partition and the probe.  (The fused peer-scatter kernel of PeerExchange moves
     the same bytes but needs every SM while it runs, so it cannot overlap a probe that also wants every SM.)
-    Cost: the regions are copied with their slack (12.5 % more NVLink bytes).  Heavily skewed keys overrun a region: this is
+    Cost: the regions are copied with their slack (3 % + two tiles more NVLink bytes; a hash partition of n rows into P regions
+    fills each to n / P +- sqrt(n / P), so even 1 % is dozens of standard deviations).  Heavily skewed keys overrun a region: this is
     detected on the device and reported by check_overflow() -- use exchange="p2p" or "nccl" for such inputs."""
 
     TILE = 4096  # region capacities are multiples of the partition kernel's tile
@@ -170,7 +171,7 @@ class CopyExchange:
         self.step = 0
         self.max_rows = int(max_rows)
         per = (self.max_rows + self.world - 1) // self.world
-        self.cap = ((per + per // 8 + 2 * self.TILE + self.TILE - 1) // self.TILE) * self.TILE  # rows per (sender, owner) region
+        self.cap = ((per + per // 32 + 2 * self.TILE + self.TILE - 1) // self.TILE) * self.TILE  # rows per (sender, owner) region
         self.rows = self.cap * self.world
         lib = pkg.lib()
         dev = torch.device("cuda", torch.cuda.current_device())
