@@ -72,6 +72,39 @@ def test_pipelined_copy_exchange_matches_direct(ccb, pg, n_sub):
     join.copier.close()
 
 
+@pytest.mark.parametrize("n_sub", [1, 3, 4])
+def test_pipelined_copy_exchange_batch_mode(ccb, pg, n_sub):
+    """ce_probe="batch" (the default beyond 2 GPUs): every sub-batch is probed as it lands; its rows go to slice b of the
+    output columns and its counters to results[b]."""
+    par = importlib.import_module(PKG_NAME + ".parallel")
+    n_build, n_probe = 1 << 22, 3 * (1 << 22) + 777
+    build = torch.arange(n_build, dtype=torch.int64, device="cuda")
+    join = par.PartitionedJoin(ccb, ccb.CC_HT_LP, build, plan="partition", exchange="ce", capacity_rows=-(-n_probe // n_sub),
+                               ce_probe="batch")
+    assert join.ce_probe == "batch"
+    keys = ccb.gen_keys_counter(n_probe, 7, 2 * n_build - 1)  # hit rate 1/2
+    hits = keys[keys < n_build]
+    want_n, want_sum = hits.numel(), int(hits.sum().item()) & ((1 << 64) - 1)
+    cap = n_probe
+    capb = cap // n_sub
+    ok = torch.empty(cap, dtype=torch.int64, device="cuda")
+    op = torch.empty(cap, dtype=torch.int64, device="cuda")
+    res = torch.zeros((n_sub, 4), dtype=torch.int64, device="cuda")
+    for rep in range(4):
+        join.probe_pipelined(keys, n_sub, ok, op, res)
+        torch.cuda.synchronize()
+        rr = res.cpu().numpy().view(np.uint64)
+        r = rr.sum(axis=0, dtype=np.uint64)
+        assert int(r[0]) == want_n and int(r[1]) == want_sum and int(r[2]) == want_sum and int(r[3]) == 0, (rep, r)
+    join.copier.check_overflow()
+    got_k = torch.cat([ok[b * capb: b * capb + int(rr[b, 0])] for b in range(n_sub)])
+    got_p = torch.cat([op[b * capb: b * capb + int(rr[b, 0])] for b in range(n_sub)])
+    assert torch.equal(torch.sort(got_k)[0], torch.sort(hits)[0]) and torch.equal(torch.sort(got_p)[0], torch.sort(hits)[0])
+    join.copier.close()
+    with pytest.raises(ValueError):
+        par.PartitionedJoin(ccb, ccb.CC_HT_LP, build, plan="broadcast", ce_probe="sometimes")
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("strategy", [1, 2])
 def test_probe_stream_equals_one_batch(ccb, kind, strategy):
