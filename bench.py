@@ -418,45 +418,49 @@ def main() -> int:
             line["e2e"] = None
             line["e2e_note"] = "pinned host buffers could not be allocated on every rank"
         else:
-            hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345 + rank * ne))
-            in_sum = int(hk.sum().item())
-            capb = cap // n_sub  # output slice of one sub-batch (p2p, ce/batch); ce/stream and nccl write one dense run from row 0
-            dense = n_sub == 1 or (args.exchange == "ce" and join.ce_probe == "stream")
+            try:  # a deterministic failure in this secondary leg must not cost the device-timed number above
+                hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345 + rank * ne))
+                in_sum = int(hk.sum().item())
+                capb = cap // n_sub  # output slice of one sub-batch (p2p, ce/batch); ce/stream and nccl write one dense run from row 0
+                dense = n_sub == 1 or (args.exchange == "ce" and join.ce_probe == "stream")
 
-            def e2e_step():
-                dk.copy_(hk, non_blocking=True)
-                step(dk)
-                counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
-                off = 0
-                for b, m in enumerate(counts):
-                    m = min(m, cap if dense else capb, hcap - off)
-                    if m:
-                        hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
-                        hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
-                    off += m
-                torch.cuda.synchronize()
-                return off
+                def e2e_step():
+                    dk.copy_(hk, non_blocking=True)
+                    step(dk)
+                    counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
+                    off = 0
+                    for b, m in enumerate(counts):
+                        m = min(m, cap if dense else capb, hcap - off)
+                        if m:
+                            hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
+                            hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
+                        off += m
+                    torch.cuda.synchronize()
+                    return off
 
-            e2e_step()
-            ts, rows = [], 0
-            for _ in range(max(3, args.steps)):
-                barrier()
-                t0 = time.perf_counter()
-                rows = e2e_step()
-                ts.append(time.perf_counter() - t0)
-            t = torch.tensor(ts, dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
-            chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
-            dist.all_reduce(chk)
-            e2e_s = float(t.mean().item())
-            if int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0:
-                line["e2e"] = {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
-                               "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of "
-                                         f"the rows each rank owns into pinned host memory (row counts read back first)",
-                               "ms_per_step": 1e3 * e2e_s}
-            else:
+                e2e_step()
+                ts, rows = [], 0
+                for _ in range(max(3, args.steps)):
+                    barrier()
+                    t0 = time.perf_counter()
+                    rows = e2e_step()
+                    ts.append(time.perf_counter() - t0)
+                t = torch.tensor(ts, dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
+                chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
+                dist.all_reduce(chk)
+                e2e_s = float(t.mean().item())
+                if int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0:
+                    line["e2e"] = {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
+                                   "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of "
+                                             f"the rows each rank owns into pinned host memory (row counts read back first)",
+                                   "ms_per_step": 1e3 * e2e_s}
+                else:
+                    line["e2e"] = None
+                    line["e2e_note"] = f"end-to-end check failed (rows, key sum out, key sum in, key != payload): {chk.tolist()}"
+            except Exception as e:  # noqa: BLE001 -- reported in the line
                 line["e2e"] = None
-                line["e2e_note"] = f"end-to-end check failed (rows, key sum out, key sum in, key != payload): {chk.tolist()}"
+                line["e2e_note"] = f"end-to-end leg failed: {type(e).__name__}: {e}"
         del hk, hok, hop, dk
 
     if rank == 0 and not args.no_cpu_baseline and not distributed:
