@@ -11,7 +11,7 @@ SM, CLK = 148, 1.92e9          # SMs, SM clock under this load (bench `clocks`)
 HBM = 6547.5e9                 # measured copy bandwidth, B/s (MEASURED_PEAKS.json)
 GATHER = 288e9                 # measured L2-resident 8-byte gathers per second (profiles/r1_gather_bench_b200.txt)
 SCATTER_MS_PER_2_31 = 9.5      # partition_scatter_kernel, 256 partitions (profiles/r1_ncu_summary.md)
-OWNER_MS_PER_2_28 = 1.12       # same kernel, 8 partitions, 2^28 keys (measured 2026-10-18, tools/ab_owner_partition run)
+OWNER_MS_PER_2_28 = 1.12       # same kernel, 8 partitions, 2^28 keys (profiles/r1_owner_partition_ballot_vs_atomics.txt)
 PROBE_MS_PER_2_31 = 17.75      # probe_unique_kernel incl. one pass over an 8 GiB table
 NVLINK_GBPS = 450e9            # fitted, see above (nominal 900 GB/s per direction)
 
