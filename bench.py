@@ -205,7 +205,6 @@ def main() -> int:
     ap.add_argument("--ce-probe", default="auto", choices=["auto", "stream", "batch"],
                     help="N>1 with --exchange ce: one incremental probe per step (stream), a probe per landed sub-batch (batch), "
                          "or stream up to 2 GPUs and batch beyond (auto)")
-    ap.add_argument("--copy-streams", type=int, default=1, help="N>1 with --exchange ce: copy streams the block copies of a shuffle are dealt onto")
     ap.add_argument("--exchange", default="ce", choices=["ce", "p2p", "nccl"],
                     help="N>1: copy-engine block copies under the probe (default), fused peer-memory scatter kernel, or NCCL all-to-all")
     args = ap.parse_args()
@@ -257,7 +256,7 @@ def main() -> int:
         local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
         cap_rows = -(-n_probe // args.sub_batches) if args.exchange == "ce" else int(n_probe * 1.05) + (1 << 20)
         join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
-                                   capacity_rows=cap_rows, peer_blocks=args.peer_blocks, ce_probe=args.ce_probe, copy_streams=args.copy_streams)
+                                   capacity_rows=cap_rows, peer_blocks=args.peer_blocks, ce_probe=args.ce_probe)
         table = join.table
         del local_build
     torch.cuda.synchronize()

@@ -161,9 +161,7 @@ class CopyExchange:
 
     TILE = 4096  # region capacities are multiples of the partition kernel's tile
 
-    def __init__(self, pkg, max_rows: int, group=None, n_buffers: int = 3, n_copy_streams: int = 1):
-        """n_copy_streams: the block copies of one shuffle are dealt round-robin onto this many copy streams (1 = the
-        measured default; more lets copies to different peers run concurrently -- untested on hardware so far)."""
+    def __init__(self, pkg, max_rows: int, group=None, n_buffers: int = 3):
         import ctypes as C
 
         self.pkg, self.group = pkg, group
@@ -203,8 +201,8 @@ class CopyExchange:
         self.mine = [torch.zeros(self.world, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
         self.overflow = torch.zeros(n_buffers, dtype=torch.int32, device=dev)
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._copy_streams = [torch.cuda.Stream() for _ in range(max(1, int(n_copy_streams)))]
-        self._copied = [None] * n_buffers  # per buffer: the events that mark its copies done (one per copy stream used)
+        self._copy_stream = torch.cuda.Stream()
+        self._copied = [None] * n_buffers
         dist.barrier(group=group)
 
     def start(self, keys: torch.Tensor) -> int:
@@ -224,29 +222,22 @@ class CopyExchange:
         parted.record(main)
         dist.all_gather_into_tensor(self.matrix[b], self.counts[b], group=self.group)  # matrix[sender * P + owner]
         self.mine[b].copy_(self.matrix[b].view(self.world, self.world)[:, self.rank])  # rows every sender delivers to this rank
-        for cs in self._copy_streams:
-            cs.wait_event(parted)
+        cs = self._copy_stream
+        cs.wait_event(parted)
         src = self.send[b].data_ptr()
         block = self.cap * 8
-        used = set()
-        for j, i in enumerate(range(0 if self.world > 16 else 1, self.world)):
+        for i in range(0 if self.world > 16 else 1, self.world):
             p = (self.rank + i) % self.world  # stagger the destinations so that the ranks do not all hit the same peer at once
-            q = j % len(self._copy_streams)
-            used.add(q)
-            pkg._lib.check(lib.cc_memcpy_d2d(self.peers[b][p] + self.rank * block, src + p * block, block, self._copy_streams[q].cuda_stream))
-        events = []
-        for q in sorted(used):
-            done = torch.cuda.Event()
-            done.record(self._copy_streams[q])
-            events.append(done)
-        self._copied[b] = events
+            pkg._lib.check(lib.cc_memcpy_d2d(self.peers[b][p] + self.rank * block, src + p * block, block, cs.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(cs)
+        self._copied[b] = done
         return k
 
     def finish(self, k: int):
         """Second half of shuffle k: returns (segmented receive column, segment capacity, device counts[P])."""
         b = k % self.n_buffers
-        for done in self._copied[b]:
-            torch.cuda.current_stream().wait_event(done)
+        torch.cuda.current_stream().wait_event(self._copied[b])
         dist.all_reduce(self._token, group=self.group)  # stream-ordered barrier: every rank's copies have landed
         return self.pkg._wrap_ptr(self.local[b], self.rows, torch.int64), self.cap, self.mine[b]
 
@@ -272,7 +263,7 @@ class PartitionedJoin:
     """Build once, probe many times.  `pkg` is the product package (passed in to avoid a circular import)."""
 
     def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition",
-                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0, ce_probe: str = "auto", copy_streams: int = 1):
+                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0, ce_probe: str = "auto"):
         """plan: "partition" (hash-partition both sides) or "broadcast" (replicate the build side).
         exchange: "nccl" (scatter locally, then all_to_all_single), "p2p" (PeerExchange: the scatter kernel
         writes into the owners' buffers over NVLink) or "ce" (CopyExchange: single-pass partition + copy-engine block
@@ -292,7 +283,7 @@ class PartitionedJoin:
         self.plan = plan
         self.ce_probe = ce_probe if ce_probe != "auto" else ("stream" if self.world <= 2 else "batch")
         self.peer = PeerExchange(pkg, capacity_rows, group, peer_blocks=peer_blocks) if (exchange == "p2p" and plan == "partition") else None
-        self.copier = CopyExchange(pkg, capacity_rows, group, n_copy_streams=copy_streams) if (exchange == "ce" and plan == "partition") else None
+        self.copier = CopyExchange(pkg, capacity_rows, group) if (exchange == "ce" and plan == "partition") else None
         T = pkg.LPHashTable if kind == pkg.CC_HT_LP else pkg.HashTable
         if plan == "broadcast":
             n_local = torch.tensor([local_build_keys.numel()], dtype=torch.int64, device=local_build_keys.device)
