@@ -107,3 +107,18 @@ def test_tuner_log_csv(tmp_path):
     files = list((tmp_path / "bandit_log").iterdir())
     assert len(files) == 1 and files[0].read_text().count("\n") >= 3
     assert t.GetBanditSize() == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/cc_api.h is the drop-in boundary: it must compile as C99 (no C++, no CUDA or torch types) and as C++17."""
+    import subprocess
+
+    src_c = tmp_path / "use_api.c"
+    src_c.write_text('#include "cc_api.h"\nint main(void) { cc_probe_result r; cc_probe_payload_result p; (void) r; (void) p; return cc_api_version() == CC_API_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_c)])
+    src_cpp = tmp_path / "use_api.cpp"
+    src_cpp.write_text(src_c.read_text())
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src_cpp)])
+    code = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S).lower()  # comments may name what a handle wraps
+    assert "cuda" not in code and "torch" not in code and "#include <std" in code
