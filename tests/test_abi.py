@@ -123,3 +123,22 @@ def test_header_is_plain_c(tmp_path):
     code = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S).lower()  # comments may name what a handle wraps
     code = code.replace("cc_err_cuda", "")  # the status code, not a type
     assert "cuda" not in code and "torch" not in code and "#include <std" in code
+
+
+def test_library_holds_sm_100a_code_only():
+    """no multi-arch fat binary, no PTX for a JIT to retarget: the product is written for B200 (sm_100a) alone, and the
+    two hot kernels use what the design says they use (TMA bulk copies in the scatter, 256-bit sector loads in the probe)"""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "chunk-compaction-in-vectorized-execution-simd_b200", "libccb200.so")
+    elfs = subprocess.check_output([cuobjdump, "--list-elf", lib], text=True).split()
+    cubins = [e for e in elfs if e.endswith(".cubin")]
+    assert cubins and all(".sm_100a." in c for c in cubins), cubins
+    sass = subprocess.check_output([cuobjdump, "-sass", lib], text=True)
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA) key ring of partition_scatter_kernel
+    assert "LDG.E.ENL2.256" in sass  # one-request sector loads of the probe's tail walk
+    assert "SYNCS" in sass           # mbarrier
