@@ -185,6 +185,77 @@ def workload_config(args) -> dict:
             "l2_policy": "inputs far exceed L2; no flush needed"}
 
 
+def distributed_e2e(dist, dev, *, ne, world, rank, n_sub, dense, cap, step, result, out_key, out_payload, gen_keys, iters):
+    """End-to-end leg at N > 1 (every rank runs it): the rank's `ne` probe keys come from pinned host memory, go to the device,
+    through `step(device_keys)` (partition + exchange + probe, writing result[n_sub, 4] and the output columns), and the rows the
+    rank ends up owning go back to pinned host memory.  dense: the step writes ONE run of rows from row 0 (counter in
+    result[0]); otherwise sub-batch b owns slice [b * cap // n_sub, ...) of the output columns and the counter result[b].
+    Returns (e2e dict or None, note or None).  The host buffers are allocated first and the ranks agree on whether all of
+    them succeeded, so that no rank enters the collectives of the timed loop alone; a deterministic failure or a failed
+    check is reported instead of costing the whole JSON line.  (Device-agnostic: tests/test_distributed_cpu.py runs it
+    under gloo on CPU tensors.)"""
+    import numpy as np
+    import torch
+
+    on_gpu = dev.type == "cuda"
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+    result.zero_()
+    hcap = ne + ne // 8 + (1 << 16)  # rows this rank can end up owning (hash partition: ne +- a fraction of a percent)
+    hk = hok = hop = dk = None
+    try:
+        hk = torch.empty(ne, dtype=torch.int64, pin_memory=on_gpu)
+        hok = torch.empty(hcap, dtype=torch.int64, pin_memory=on_gpu)
+        hop = torch.empty(hcap, dtype=torch.int64, pin_memory=on_gpu)
+        dk = torch.empty(ne, dtype=torch.int64, device=dev)
+        ready = 1
+    except Exception:
+        ready = 0
+    flag = torch.tensor([ready], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return None, "pinned host buffers could not be allocated on every rank"
+    try:
+        hk.copy_(gen_keys(ne, 12345 + rank * ne))
+        in_sum = int(hk.sum().item())
+        capb = cap // n_sub
+
+        def e2e_step():
+            dk.copy_(hk, non_blocking=True)
+            step(dk)
+            counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
+            off = 0
+            for b, m in enumerate(counts):
+                m = min(m, cap if dense else capb, hcap - off)
+                if m:
+                    hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
+                    hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
+                off += m
+            sync()
+            return off
+
+        e2e_step()
+        ts, rows = [], 0
+        for _ in range(iters):
+            dist.barrier()
+            sync()
+            t0 = time.perf_counter()
+            rows = e2e_step()
+            ts.append(time.perf_counter() - t0)
+        t = torch.tensor(ts, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
+        chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
+        dist.all_reduce(chk)
+        e2e_s = float(t.mean().item())
+        if not (int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0):
+            return None, f"end-to-end check failed (rows, key sum out, key sum in, key != payload): {chk.tolist()}"
+        return {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
+                "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of "
+                          f"the rows each rank owns into pinned host memory (row counts read back first)",
+                "ms_per_step": 1e3 * e2e_s}, None
+    except Exception as e:  # noqa: BLE001 -- reported in the line
+        return None, f"end-to-end leg failed: {type(e).__name__}: {e}"
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -397,71 +468,14 @@ def main() -> int:
     elif distributed and args.no_e2e:
         line["e2e"] = None
     elif distributed:
-        # every rank: its probe keys come from pinned host memory, the rows it ends up owning go back to pinned host memory.
-        # The buffers are allocated first and the ranks agree on whether all of them succeeded, so that no rank can enter
-        # the collectives of the timed loop alone; a failed check reports e2e = null instead of losing the whole line.
-        result.zero_()
-        ne = 1 << min(args.e2e_log2_probe - 1, args.log2_probe)
-        hk = hok = hop = dk = None
-        try:
-            hk = torch.empty(ne, dtype=torch.int64, pin_memory=True)
-            hcap = ne + ne // 8 + (1 << 16)  # rows this rank can end up owning (hash partition: ne +- a fraction of a percent)
-            hok = torch.empty(hcap, dtype=torch.int64, pin_memory=True)
-            hop = torch.empty(hcap, dtype=torch.int64, pin_memory=True)
-            dk = torch.empty(ne, dtype=torch.int64, device=dev)
-            ready = 1
-        except Exception:
-            ready = 0
-        flag = torch.tensor([ready], dtype=torch.int64, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            line["e2e"] = None
-            line["e2e_note"] = "pinned host buffers could not be allocated on every rank"
-        else:
-            try:  # a deterministic failure in this secondary leg must not cost the device-timed number above
-                hk.copy_(pkg.gen_keys_counter(ne, 2, key_space - 1, first=12345 + rank * ne))
-                in_sum = int(hk.sum().item())
-                capb = cap // n_sub  # output slice of one sub-batch (p2p, ce/batch); ce/stream and nccl write one dense run from row 0
-                dense = n_sub == 1 or (args.exchange == "ce" and join.ce_probe == "stream")
-
-                def e2e_step():
-                    dk.copy_(hk, non_blocking=True)
-                    step(dk)
-                    counts = [int(c) for c in result.cpu().numpy().view(np.uint64)[:, 0]]  # the host must learn the row counts: part of the cost
-                    off = 0
-                    for b, m in enumerate(counts):
-                        m = min(m, cap if dense else capb, hcap - off)
-                        if m:
-                            hok[off:off + m].copy_(out_key[b * capb:b * capb + m], non_blocking=True)
-                            hop[off:off + m].copy_(out_payload[b * capb:b * capb + m], non_blocking=True)
-                        off += m
-                    torch.cuda.synchronize()
-                    return off
-
-                e2e_step()
-                ts, rows = [], 0
-                for _ in range(max(3, args.steps)):
-                    barrier()
-                    t0 = time.perf_counter()
-                    rows = e2e_step()
-                    ts.append(time.perf_counter() - t0)
-                t = torch.tensor(ts, dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every step ends when its slowest rank is done
-                chk = torch.tensor([rows, int(hok[:rows].sum().item()), in_sum, int((hok[:rows] != hop[:rows]).sum().item())], dtype=torch.int64, device=dev)
-                dist.all_reduce(chk)
-                e2e_s = float(t.mean().item())
-                if int(chk[0]) == ne * world and int(chk[1]) == int(chk[2]) and int(chk[3]) == 0:
-                    line["e2e"] = {"value": ne * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ne * 8 * world, "d2h_bytes_per_step": (16 * ne + 32 * n_sub) * world,
-                                   "sample": f"2^{ne.bit_length() - 1} probe keys per GPU and call: pinned host keys -> H2D -> partition + exchange + probe -> D2H of "
-                                             f"the rows each rank owns into pinned host memory (row counts read back first)",
-                                   "ms_per_step": 1e3 * e2e_s}
-                else:
-                    line["e2e"] = None
-                    line["e2e_note"] = f"end-to-end check failed (rows, key sum out, key sum in, key != payload): {chk.tolist()}"
-            except Exception as e:  # noqa: BLE001 -- reported in the line
-                line["e2e"] = None
-                line["e2e_note"] = f"end-to-end leg failed: {type(e).__name__}: {e}"
-        del hk, hok, hop, dk
+        e2e, note = distributed_e2e(dist, dev, ne=1 << min(args.e2e_log2_probe - 1, args.log2_probe), world=world, rank=rank, n_sub=n_sub,
+                                    dense=n_sub == 1 or (args.exchange == "ce" and join.ce_probe == "stream"), cap=cap, step=step,
+                                    result=result, out_key=out_key, out_payload=out_payload,
+                                    gen_keys=lambda n, first: pkg.gen_keys_counter(n, 2, key_space - 1, first=first),
+                                    iters=max(3, args.steps))
+        line["e2e"] = e2e
+        if note:
+            line["e2e_note"] = note
 
     if rank == 0 and not args.no_cpu_baseline and not distributed:
         try:

@@ -90,3 +90,82 @@ def test_plan_rule_and_log2():
     # a 2M-key build against 8B probe keys is broadcast; 1B build against 8B probe is partitioned (C5)
     assert par.choose_plan(2_000_000, 8 << 30, 8) == "broadcast"
     assert par.choose_plan(1 << 30, 8 << 30, 8) == "partition"
+
+
+def _e2e_worker(rank: int, world: int, port: int, q):
+    """bench.distributed_e2e under gloo: the step is a CPU stand-in (modulo partition + the real exchange helpers + an
+    identity 'probe'), what is under test is the leg's own accounting -- H2D / D2H slicing, counters, cross-rank checks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    import bench
+
+    par = importlib.import_module(PKG_NAME + ".parallel")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cpu")
+        ne, n_sub = 1 << 12, 4
+        cap = (ne * 2 // n_sub) * n_sub
+        capb = cap // n_sub
+        out_key = torch.zeros(cap, dtype=torch.int64)
+        out_payload = torch.zeros(cap, dtype=torch.int64)
+        result = torch.zeros((n_sub, 4), dtype=torch.int64)
+
+        def make_step(dense, corrupt=False):
+            def step(dk):
+                result.zero_()
+                off = 0
+                for b, chunk in enumerate(np.array_split(dk.numpy(), n_sub)):
+                    pid = chunk % world
+                    order = np.argsort(pid, kind="stable")
+                    counts = np.bincount(pid, minlength=world).astype(np.int64)
+                    recv_counts = par.exchange_counts(torch.from_numpy(counts))
+                    got = par.exchange_rows(torch.from_numpy(chunk[order].copy()), counts.tolist(), recv_counts.tolist())
+                    m = got.numel()
+                    at = off if dense else b * capb
+                    out_key[at:at + m] = got
+                    out_payload[at:at + m] = got + (1 if corrupt and b == 1 else 0)
+                    if dense:
+                        off += m
+                        result[0, 0] += m
+                    else:
+                        result[b, 0] = m
+            return step
+
+        gen = lambda n, first: torch.arange(first, first + n, dtype=torch.int64)
+        for dense in (True, False):
+            e2e, note = bench.distributed_e2e(dist, dev, ne=ne, world=world, rank=rank, n_sub=n_sub, dense=dense, cap=cap, step=make_step(dense),
+                                              result=result, out_key=out_key, out_payload=out_payload, gen_keys=gen, iters=2)
+            assert note is None and e2e is not None, note
+            assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == ne * 8 * world and e2e["d2h_bytes_per_step"] == (16 * ne + 32 * n_sub) * world
+        e2e, note = bench.distributed_e2e(dist, dev, ne=ne, world=world, rank=rank, n_sub=n_sub, dense=False, cap=cap, step=make_step(False, corrupt=True),
+                                          result=result, out_key=out_key, out_payload=out_payload, gen_keys=gen, iters=1)
+        assert e2e is None and "check failed" in note
+
+        def broken(dk):
+            raise RuntimeError("boom")
+
+        e2e, note = bench.distributed_e2e(dist, dev, ne=ne, world=world, rank=rank, n_sub=n_sub, dense=True, cap=cap, step=broken,
+                                          result=result, out_key=out_key, out_payload=out_payload, gen_keys=gen, iters=1)
+        assert e2e is None and "boom" in note
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_distributed_e2e_leg_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 77
+    procs = [ctx.Process(target=_e2e_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, "ok") for r in range(world)], results
