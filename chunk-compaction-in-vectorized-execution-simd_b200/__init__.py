@@ -279,7 +279,7 @@ class _TableBase:
     kind = -1
 
     def __init__(self, n_rhs_tuples: Optional[int] = None, chunk_factor: int = 1, *, keys=None, flags: int = CC_BUILD_ORDERED,
-                 payload=None, keep_payload: bool = False):
+                 payload=None, keep_payload: bool = False, n_slots: int = 0):
         """HashTable(n_rhs_tuples, chunk_factor) like the reference (chaining_ht.h:88), or keys=... for explicit
         build keys (the reference has no external build-input API).
         Payload columns: payload=[col, ...] with keys=..., or keep_payload=True to keep the column the
@@ -288,7 +288,7 @@ class _TableBase:
         h = C.c_void_p()
         if keys is not None:
             k = _i64(keys)
-            L.check(lib().cc_ht_build(C.byref(h), self.kind, _ptr(k) if k.numel() else None, k.numel(), flags, _stream()))
+            L.check(lib().cc_ht_build_sized(C.byref(h), self.kind, _ptr(k) if k.numel() else None, k.numel(), int(n_slots), flags, _stream()))
             self._h = h.value
             if payload is not None:
                 self.attach_payload(k, payload)

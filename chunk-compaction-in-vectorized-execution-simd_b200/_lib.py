@@ -108,11 +108,14 @@ SIGNATURES = {
     "cc_stream_create": (_int, [_pvp]),
     "cc_stream_destroy": (_int, [_vp]),
     "cc_stream_sync": (_int, [_vp]),
+    "cc_scratch_set_retention": (_int, [_u64]),
+    "cc_scratch_release": (_int, []),
     "cc_launch_count": (_u64, []),
     "cc_hash_u64": (_int, [_vp, _vp, _sz, _vp]),
     "cc_gen_build_keys": (_int, [_vp, _sz, _sz, _vp]),
     "cc_gen_keys_counter": (_int, [_vp, _sz, _u64, _u64, _u64, _vp]),
     "cc_ht_build": (_int, [_pvp, _int, _vp, _sz, _int, _vp]),
+    "cc_ht_build_sized": (_int, [_pvp, _int, _vp, _sz, _sz, _int, _vp]),
     "cc_ht_build_reference": (_int, [_pvp, _int, _sz, _sz, _vp]),
     "cc_ht_import_lp": (_int, [_pvp, _vp, _sz, _sz, _vp]),
     "cc_ht_attach_payload": (_int, [_vp, _vp, _pvp, _sz, _vp]),

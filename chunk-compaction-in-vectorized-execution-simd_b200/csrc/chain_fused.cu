@@ -27,6 +27,9 @@
 // (chaining_ht.cpp:34 drops the payload column), so an intermediate row is fully
 // described by its LHS row id; the result tuple [k_0..k_{J-1}, 0,k_0, 0,k_1, ...]
 //  is rebuilt from the LHS columns at the ResultCollector.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ccb {
@@ -327,6 +330,350 @@ __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-granular form of the same state machine (the default).  ONE WARP is one pipeline instance: a chunk is kR rows per
+// lane (W = 32 * kR rows), every __syncthreads() of the CTA-wide kernel becomes a __syncwarp(), the three block-wide scans
+// of a round become ballots / one packed warp scan, and warps never wait for each other -- while one instance sits on a
+// table gather the others rank, compact and probe.  (The CTA-wide kernel spent its time at 6-10 barriers per step with
+// every thread of the SM waiting for the same loads at the same moment: 2.8 us per step, profiles/r1_chain_c3_thresholds.txt.)
+// A lane keeps kR independent gathers in flight in a probe step and kR * kS in a round; checksums are accumulated in
+// registers over the whole kernel instead of being warp-reduced into shared memory every round.
+// Thresholds keep their meaning on the CC_CHAIN_WIDTH = 512-row scale: need = ceil(threshold * W / 512), clamped to [1, W].
+struct WarpShared {
+  unsigned long long level_in[CC_MAX_JOINS], steps[CC_MAX_JOINS], lanes[CC_MAX_JOINS];
+  uint32_t bufcnt[CC_MAX_JOINS + 1];
+  uint32_t active[CC_MAX_JOINS];
+};
+
+template <int R>
+__global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
+  static_assert(R >= 1 && R <= 4, "the match ranks of a round are packed into four 16-bit fields");
+  constexpr int W = 32 * R;       // rows per chunk of this pipeline instance
+  constexpr int SC = 2 * W;       // scan[L]: a probe step may add W lanes to W - 1 waiting ones
+  constexpr int BC = 5 * W;       // chunk[L]: rounds are narrowed so that their matches always fit (see `limit`)
+  constexpr int KSC = 8;          // chain entries inspected per lane and round (two sectors: a 5-entry chain ends in one round)
+  constexpr int KSL = 4;          // LP slots inspected per lane and round
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpShared &S = *reinterpret_cast<WarpShared *>(smem_raw);
+  uint32_t *sc_row = reinterpret_cast<uint32_t *>(smem_raw + sizeof(WarpShared));  // [J][SC]
+  uint32_t *sc_pos = sc_row + a.n_joins * SC;
+  uint32_t *sc_end = sc_pos + a.n_joins * SC;
+  uint32_t *bufs = sc_end + a.n_joins * SC;  // chunk[L] for L = 1 .. J-1 at bufs + (L-1)*BC
+  const int J = a.n_joins;
+  const unsigned lane = threadIdx.x, lt = lanemask_lt();
+  const auto need_of = [&](int l) -> uint32_t {  // threshold of the compactor behind join l, on this instance's chunk width
+    const uint32_t t = (a.lv[l].need * (uint32_t) W + (uint32_t) kW - 1u) / (uint32_t) kW;
+    return t < 1u ? 1u : (t > (uint32_t) W ? (uint32_t) W : t);
+  };
+
+  if (lane == 0) {
+    for (int j = 0; j < CC_MAX_JOINS; ++j) S.level_in[j] = S.steps[j] = S.lanes[j] = 0, S.active[j] = 0;
+    for (int j = 0; j <= CC_MAX_JOINS; ++j) S.bufcnt[j] = 0;
+    atomicMin((unsigned long long *) &a.res->reserved[1], (unsigned long long) globaltimer_ns());
+  }
+  __syncwarp();
+
+  uint64_t cs_acc[CC_MAX_JOINS];  // per-lane partial column sums / digest of the result rows, reduced once at the end
+#pragma unroll
+  for (int j = 0; j < CC_MAX_JOINS; ++j) cs_acc[j] = 0;
+  uint64_t digest_acc = 0;
+
+  const size_t ntiles = (a.n_rows + W - 1) / W;
+  int cur = 0;
+  bool exhausted = false;
+  int flush_upto = 0;
+
+  for (;;) {
+    // ---- 1. descend: the compactor in front of level cur+1 holds a chunk (or is being flushed)
+    if (cur + 1 < J) {
+      const uint32_t cnt = S.bufcnt[cur + 1];
+      const uint32_t need = (cur + 1 <= flush_upto) ? 1u : need_of(cur);
+      if (cnt >= need) {
+        ++cur;
+        continue;
+      }
+    }
+    const uint32_t n_act = S.active[cur];
+    const bool has_input = cur == 0 ? !exhausted : S.bufcnt[cur] > 0;
+    const uint32_t want = need_of(cur > 0 ? cur - 1 : 0);
+    const bool closed = cur == 0 ? exhausted : cur <= flush_upto;
+    // ---- 2. round (Next): ScanInnerJoin + GatherResult + AdvancePointers for up to W waiting lanes
+    if (n_act >= want || (n_act > 0 && !has_input && closed)) {
+      const int L = cur;
+      const ChainLevel &lv = a.lv[L];
+      const bool chain = lv.kind == CC_HT_CHAIN;
+      const uint32_t ks = chain ? (uint32_t) KSC : (uint32_t) KSL;
+      uint32_t limit = (uint32_t) W;
+      if (L + 1 < J) {  // every lane may emit ks matches: take only as many lanes as the next chunk can absorb
+        const uint32_t room = ((uint32_t) BC - S.bufcnt[L + 1]) / ks;
+        limit = room < limit ? room : limit;
+      }
+      const uint32_t lanes = n_act < limit ? n_act : limit;
+      const uint32_t first = n_act - lanes;  // the LAST `lanes` entries of the scan are processed
+      uint32_t row[R], p[R], e[R], m[R];
+      bool still[R];
+      uint64_t key[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const uint32_t idx = (uint32_t) i * 32u + lane;
+        row[i] = kNoRow;
+        p[i] = e[i] = m[i] = 0;
+        still[i] = false;
+        if (idx < lanes) {
+          row[i] = sc_row[L * SC + first + idx];
+          p[i] = sc_pos[L * SC + first + idx];
+          e[i] = sc_end[L * SC + first + idx];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) key[i] = row[i] != kNoRow ? (uint64_t) __ldg(lv.col + row[i]) : 0ull;
+      if (chain) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          if (row[i] != kNoRow) {
+            uint64_t v[KSC];
+#pragma unroll
+            for (int q = 0; q < KSC; ++q) v[q] = (p[i] + q < e[i]) ? (uint64_t) __ldg(lv.ckeys + p[i] + q) : ~key[i];
+#pragma unroll
+            for (int q = 0; q < KSC; ++q) m[i] += (p[i] + q < e[i]) && (v[q] == key[i]);
+            p[i] = (e[i] - p[i] > (uint32_t) KSC) ? p[i] + KSC : e[i];
+            still[i] = p[i] != e[i];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          if (row[i] != kNoRow) {
+            uint64_t v[KSL];
+#pragma unroll
+            for (int q = 0; q < KSL; ++q) v[q] = ld_nc_u64(lv.slots + ((uint64_t) (p[i] + q) & lv.mask));
+            bool open = true;
+#pragma unroll
+            for (int q = 0; q < KSL; ++q) {
+              open = open && v[q] != kEmptyU;  // the walk ends at the first empty slot (linear_probing_ht.cpp:104-108)
+              m[i] += (open && v[q] == key[i]) ? 1u : 0u;
+            }
+            still[i] = open;
+            p[i] = (uint32_t) ((uint64_t) (p[i] + KSL) & lv.mask);
+          }
+        }
+      }
+      if (lv.unique) {
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          if (m[i]) still[i] = false;
+      }
+      __syncwarp();  // every lane has read its scan entries: the tail may be rewritten
+      // AdvancePointers: surviving lanes stay in the scan, compacted in place at the tail
+      uint32_t sbase = first;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const unsigned bal = __ballot_sync(0xffffffffu, still[i]);
+        if (still[i]) {
+          const uint32_t o = sbase + __popc(bal & lt);
+          sc_row[L * SC + o] = row[i];
+          sc_pos[L * SC + o] = p[i];
+          sc_end[L * SC + o] = e[i];
+        }
+        sbase += __popc(bal);
+      }
+      // rank the matches: ONE warp scan over the kR per-lane counts packed into 16-bit fields (a field sums to <= 32 * 8)
+      uint64_t packed = 0;
+#pragma unroll
+      for (int i = 0; i < R; ++i) packed |= (uint64_t) m[i] << (16 * i);
+      uint64_t incl = packed;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned) o) incl += t;
+      }
+      const uint64_t tot = __shfl_sync(0xffffffffu, incl, 31);
+      const uint64_t excl = incl - packed;
+      uint32_t off[R], total = 0;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        off[i] = total + (uint32_t) ((excl >> (16 * i)) & 0xFFFFu);
+        total += (uint32_t) ((tot >> (16 * i)) & 0xFFFFu);
+      }
+      if (L + 1 < J) {
+        // Compact: append the matching rows densely to the next level's cached chunk
+        const uint32_t cnt0 = S.bufcnt[L + 1];
+        uint32_t *dst = bufs + L * BC + cnt0;
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          for (uint32_t q = 0; q < m[i]; ++q) dst[off[i] + q] = row[i];
+        __syncwarp();
+        if (lane == 0) S.bufcnt[L + 1] = cnt0 + total;
+      } else if (total) {
+        // ResultCollector (main.cpp:125-128, data_collection.cpp:10-21)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd((unsigned long long *) &a.res->n_tuples, (unsigned long long) total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          if (m[i]) {
+            uint64_t th = 0x9e3779b97f4a7c15ULL;
+            for (int j = 0; j < 3 * J; ++j) {
+              const uint64_t v = j < J ? (uint64_t) __ldg(a.lv[j].col + row[i]) : (((j - J) & 1) ? (uint64_t) __ldg(a.lv[(j - J) >> 1].col + row[i]) : 0ull);
+              th = murmurhash64(th ^ v) + (uint64_t) j;
+            }
+            digest_acc += th * (uint64_t) m[i];
+#pragma unroll
+            for (int j = 0; j < CC_MAX_JOINS; ++j)
+              if (j < J) cs_acc[j] += (uint64_t) __ldg(a.lv[j].col + row[i]) * (uint64_t) m[i];
+            if (a.materialize) {
+              const uint64_t at = base + off[i];
+              for (int j = 0; j < 3 * J; ++j) {
+                const int64_t v = j < J ? __ldg(a.lv[j].col + row[i]) : (((j - J) & 1) ? __ldg(a.lv[(j - J) >> 1].col + row[i]) : 0ll);
+                for (uint32_t q = 0; q < m[i]; ++q)
+                  if (at + q < a.cap) a.out[j][at + q] = v;
+              }
+            }
+          }
+        }
+      }
+      if (lane == 0) {
+        S.active[L] = sbase;
+        S.steps[L] += 1;
+        S.lanes[L] += (unsigned long long) lanes;
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- 3. probe step (Probe, chaining_ht.cpp:38-58 / linear_probing_ht.cpp:39-60): refill the scan of level cur; only
+    //         lanes with a non-empty bucket / first slot enter it, appended densely behind the lanes already waiting
+    if (has_input) {
+      const int L = cur;
+      const ChainLevel &lv = a.lv[L];
+      uint32_t row[R];
+      if (L == 0) {
+        unsigned long long tile = 0;
+        if (lane == 0) tile = atomicAdd((unsigned long long *) &a.res->reserved[0], 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= (unsigned long long) ntiles) {
+          exhausted = true;
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const size_t r = (size_t) tile * W + (size_t) i * 32 + lane;
+          row[i] = r < a.n_rows ? (uint32_t) r : kNoRow;
+        }
+      } else {
+        const uint32_t cnt = S.bufcnt[L];
+        const uint32_t take = cnt < (uint32_t) W ? cnt : (uint32_t) W;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const uint32_t idx = (uint32_t) i * 32u + lane;
+          row[i] = idx < take ? bufs[(L - 1) * BC + (cnt - take) + idx] : kNoRow;
+        }
+        __syncwarp();
+        if (lane == 0) S.bufcnt[L] = cnt - take;
+      }
+      uint64_t h[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) h[i] = row[i] != kNoRow ? (murmurhash64((uint64_t) __ldg(lv.col + row[i])) & lv.mask) : 0ull;
+      uint32_t pos[R], end[R];
+      bool act[R];
+      if (lv.kind == CC_HT_CHAIN) {
+        uint2 d[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) d[i] = row[i] != kNoRow ? __ldg(lv.dir + h[i]) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          pos[i] = d[i].x;
+          end[i] = d[i].x + d[i].y;
+          act[i] = d[i].y != 0;
+        }
+      } else {
+        uint64_t v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = row[i] != kNoRow ? ld_nc_u64(lv.slots + h[i]) : kEmptyU;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          pos[i] = (uint32_t) h[i];
+          end[i] = 0;
+          act[i] = v[i] != kEmptyU;
+        }
+      }
+      uint32_t n_valid = 0;
+      uint32_t base = S.active[L];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        n_valid += __popc(__ballot_sync(0xffffffffu, row[i] != kNoRow));
+        const unsigned bal = __ballot_sync(0xffffffffu, act[i]);
+        if (act[i]) {
+          const uint32_t o = base + __popc(bal & lt);
+          sc_row[L * SC + o] = row[i];
+          sc_pos[L * SC + o] = pos[i];
+          sc_end[L * SC + o] = end[i];
+        }
+        base += __popc(bal);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        S.active[L] = base;
+        S.level_in[L] += (unsigned long long) n_valid;
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- 4. level cur has no input (and no lanes, or too few while its upstream can still deliver)
+    if (cur > 0) {
+      --cur;
+      continue;
+    }
+    // level 0 idle and the table exhausted: FlushPipelineCache (main.cpp:172-191) -- drain the caches top-down
+    {
+      int next = 0;
+      for (int l = 1; l < J; ++l)
+        if (S.bufcnt[l] > 0 || S.active[l] > 0) {
+          next = l;
+          break;
+        }
+      if (next == 0) break;
+      flush_upto = next;
+      cur = next;
+    }
+  }
+
+  __syncwarp();
+  digest_acc = warp_sum_u64(digest_acc);
+#pragma unroll
+  for (int j = 0; j < CC_MAX_JOINS; ++j) cs_acc[j] = j < J ? warp_sum_u64(cs_acc[j]) : 0ull;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < CC_MAX_JOINS; ++j) {
+      if (j < J) {
+        if (cs_acc[j]) {
+          atomicAdd((unsigned long long *) &a.res->colsum[j], (unsigned long long) cs_acc[j]);
+          atomicAdd((unsigned long long *) &a.res->colsum[J + 2 * j + 1], (unsigned long long) cs_acc[j]);
+        }
+        if (S.level_in[j]) atomicAdd((unsigned long long *) &a.res->level_in[j], S.level_in[j]);
+        if (S.steps[j]) atomicAdd((unsigned long long *) &a.res->level_steps[j], S.steps[j]);
+        if (S.lanes[j]) atomicAdd((unsigned long long *) &a.res->level_lanes[j], S.lanes[j]);
+      }
+    }
+    if (digest_acc) atomicAdd((unsigned long long *) &a.res->digest, (unsigned long long) digest_acc);
+    atomicMax((unsigned long long *) &a.res->reserved[2], (unsigned long long) globaltimer_ns());
+  }
+}
+
+template <int R>
+static int launch_chain_warp(const ChainArgs &a, size_t n_joins, cudaStream_t st) {
+  constexpr int W = 32 * R;
+  const size_t smem = sizeof(WarpShared) + n_joins * 3 * (size_t) (2 * W) * sizeof(uint32_t) + (n_joins - 1) * (size_t) (5 * W) * sizeof(uint32_t);
+  CC_CUDA(cudaFuncSetAttribute(chain_warp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  int per_sm = 0;
+  CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_warp_kernel<R>, 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const size_t ntiles = (a.n_rows + W - 1) / W;
+  const size_t grid = std::min<size_t>(ntiles, (size_t) sm_count() * per_sm);
+  chain_warp_kernel<R><<<(unsigned) grid, 32, smem, st>>>(a);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
 __global__ void chain_finish_kernel(cc_chain_result *res, size_t cap, int materialize) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     res->overflow = (materialize && res->n_tuples > cap) ? 1 : 0;
@@ -380,7 +727,18 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
   CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_chain_result), st));
   chain_init_kernel<<<1, 32, 0, st>>>(d_result);
   CC_CHECK_LAUNCH();
-  if (n_rows) {
+  // measurement switch: CCB_CHAIN_IMPL = cta (the round-1 CTA-wide kernel), w1 / w2 / w4 (warp pipelines, rows per lane); default w4
+  static const int impl = [] {
+    const char *e = getenv("CCB_CHAIN_IMPL");
+    if (!e) return 4;
+    if (!strcmp(e, "cta")) return 0;
+    if (!strcmp(e, "w2")) return 2;
+    if (!strcmp(e, "w1")) return 1;
+    return 4;
+  }();
+  if (n_rows && impl != 0) {
+    CC_TRY(impl == 1 ? launch_chain_warp<1>(a, n_joins, st) : impl == 2 ? launch_chain_warp<2>(a, n_joins, st) : launch_chain_warp<4>(a, n_joins, st));
+  } else if (n_rows) {
     size_t smem = sizeof(ChainShared) + n_joins * 3 * (size_t) kScanCap * sizeof(uint32_t) + (n_joins - 1) * (size_t) kBufCap * sizeof(uint32_t);
     CC_CUDA(cudaFuncSetAttribute(chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int per_sm = 0;

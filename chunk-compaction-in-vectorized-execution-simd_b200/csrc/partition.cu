@@ -344,11 +344,13 @@ __global__ void partition_seg_prefix_kernel(const unsigned long long *__restrict
 
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
                             int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg, bool accumulate,
-                            int self_part, int64_t *d_self_out) {
+                            int self_part, int64_t *d_self_out, bool sticky_flag) {
   const int parts = (int) fn.pmask + 1;
   if (!accumulate) {
     CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
-    CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    // sticky_flag: the kernel only ever ORs into *d_flag, so an overrun reported by an EARLIER call survives until the caller
+    // has looked at it (the copy-engine exchange reuses one flag for many shuffles and checks once per step)
+    if (!sticky_flag) CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   }
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   if (blocks == 0) blocks = 1;
@@ -445,7 +447,7 @@ int cc_partition_single(const int64_t *d_keys, size_t n, int log2_parts, size_t 
   CC_REQUIRE(d_counts && d_overflow && d_out && (n == 0 || d_keys), "NULL argument");
   CC_REQUIRE(region_capacity > 0, "region_capacity must be positive");
   return partition_single_device(d_keys, n, PartFn::high_bits(log2_parts), region_capacity, (unsigned long long *) d_counts, d_overflow, 0,
-                                 nullptr, d_out, as_stream(s), SegIn(), false, self_part, d_self_out);
+                                 nullptr, d_out, as_stream(s), SegIn(), false, self_part, d_self_out, /*sticky_flag=*/true);
 }
 
 static int g_peer_blocks = 0;  // 0 = fill the GPU; > 0 = CTA cap of the peer scatter (it is NVLink-bound)

@@ -59,7 +59,7 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
 // two-pass fallback takes over); d_prefix[0 .. parts] = exclusive prefix of the per-partition tile counts (seg_tile rows each).
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
                             int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg = SegIn(),
-                            bool accumulate = false, int self_part = -1, int64_t *d_self_out = nullptr);
+                            bool accumulate = false, int self_part = -1, int64_t *d_self_out = nullptr, bool sticky_flag = false);
 // accumulate: keep cursors / flag of earlier calls (the regions fill up over several inputs)
 // d_prefix[0 .. parts] = exclusive prefix of ceil(min(d_cursors[p], cap_rows) / seg_tile) (the probe kernel's tile directory)
 int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,

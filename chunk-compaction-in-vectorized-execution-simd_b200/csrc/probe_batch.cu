@@ -814,6 +814,256 @@ __global__ void __launch_bounds__(kPbThreads, CCB_LEAN_MIN_BLOCKS) probe_unique_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// probe_unique_lp_kernel: the lean kernel for LP tables with the tail walk DEFERRED through a persistent per-warp queue.
+// probe_unique_kernel resolves the ~13 % of keys whose home slot holds another key inside the same iteration: a second
+// dependent L2 round trip per tile for all of them, a third for the ~3 % that need another sector (nearly every warp has one),
+// and the CTA waits at the tile barrier for its slowest warp (ncu, round 1: 17 % of all stall samples on the tail walk's
+// LDG.256, 16.5 % at the barrier).  Here an unresolved key is pushed into a small per-warp ring (key, next slot); every
+// iteration each lane pops at most ONE pending entry and loads its sector TOGETHER with the tile's home-slot gathers, so an
+// iteration has exactly one load phase whatever the probe sequences look like.  An entry that is still unresolved after its
+// sector goes back into the ring; matches found by the tail are parked with the matches of the tile that is being probed when
+// they resolve (row order is unspecified).  When the key column is exhausted the CTA keeps iterating without a tile until
+// every ring has drained.  Ring overflow (more than kRingCap pending keys: only adversarial key sets) falls back to walking
+// the excess keys to completion on the spot, like the generic kernel does.
+constexpr int kRingCap = 64;
+struct __align__(16) LeanLpShared {
+  uint32_t cnt[2][kPbWarps];
+  unsigned long long base[2];
+  unsigned long long off[2];
+  uint32_t rows[2];
+  uint32_t seg_p, seg_lo, seg_hi, seg_total;
+  unsigned long long seg_cnt;
+  uint64_t ring_key[kPbWarps][kRingCap];
+  uint32_t ring_at[kPbWarps][kRingCap];
+  // per-warp parking area of the matches of one iteration (at most 128 home matches + 32 tail matches)
+  uint64_t stage[kPbWarps][kPbKeysPerThread * 32 + 32];
+};
+
+template <class SH>
+__device__ __forceinline__ void lean_tile_t(const ProbeArgs &a, SH &sh, unsigned long long g, unsigned long long &off, uint32_t &rows) {
+  off = 0;
+  rows = 0;
+  if (a.seg_parts == 0) {
+    const unsigned long long ntiles = (a.n + kPbTile - 1) / kPbTile;
+    if (g >= ntiles) return;
+    off = g * (unsigned long long) kPbTile;
+    rows = (uint32_t) (a.n - off < (unsigned long long) kPbTile ? a.n - off : (unsigned long long) kPbTile);
+    return;
+  }
+  if (g >= sh.seg_total) return;
+  uint32_t p = sh.seg_p, lo = sh.seg_lo, hi = sh.seg_hi;
+  if ((uint32_t) g >= hi) {
+    do {
+      ++p;
+      lo = hi;
+      hi = __ldg(a.seg_prefix + p + 1);
+    } while ((uint32_t) g >= hi);
+    unsigned long long c = __ldg(a.seg_cursors + p);
+    sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
+    sh.seg_p = p;
+    sh.seg_lo = lo;
+    sh.seg_hi = hi;
+  }
+  const unsigned long long first = (unsigned long long) ((uint32_t) g - lo) * kPbTile;
+  const unsigned long long left = sh.seg_cnt - first;
+  off = (unsigned long long) p * a.seg_cap + first;
+  rows = left < (unsigned long long) kPbTile ? (uint32_t) left : (uint32_t) kPbTile;
+}
+
+template <int MODE, int OUT>
+__global__ void __launch_bounds__(kPbThreads, CCB_LEAN_MIN_BLOCKS) probe_unique_lp_kernel(ProbeArgs a) {
+  __shared__ LeanLpShared sh;
+  const CachePolicy pol = make_policies();
+  if (a.gate && ((*a.gate != 0) != (a.gate_want != 0))) return;  // device-side strategy switch (CTA-uniform)
+  const uint32_t mask = (uint32_t) a.mask;
+  const unsigned lane = lane_id(), w = threadIdx.x >> 5, lt = lanemask_lt();
+  const unsigned outsel = OUT >= 0 ? (unsigned) OUT : ((a.out_key ? 1u : 0u) | (a.out_payload ? 2u : 0u) | (a.out_rowid ? 4u : 0u));
+  uint64_t ksum = 0;
+  if (threadIdx.x == 0) {
+    if (a.seg_parts) {
+      unsigned long long c = a.seg_cursors[0];
+      sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
+      sh.seg_p = 0;
+      sh.seg_lo = 0;
+      sh.seg_hi = a.seg_prefix[1];
+      sh.seg_total = a.seg_prefix[a.seg_parts];
+    }
+    lean_tile_t(a, sh, atomicAdd(a.tile_counter, 1ull), sh.off[0], sh.rows[0]);
+    lean_tile_t(a, sh, atomicAdd(a.tile_counter, 1ull), sh.off[1], sh.rows[1]);
+  }
+  __syncthreads();
+  unsigned long long off = sh.off[0], noff = sh.off[1];
+  uint32_t rows = sh.rows[0], nrows = sh.rows[1];
+  __syncthreads();
+  uint64_t kn[kPbKeysPerThread];
+  lean_load_keys<MODE>(a, pol, off, rows, kn);
+  unsigned par = 0;
+  uint32_t prev_woff = 0, prev_cnt = 0;   // this warp's share of the previous iteration's output range
+  unsigned long long pending = 0;         // thread 0: output base of the previous iteration (result of its atomicAdd)
+  uint32_t rhead = 0, rn = 0;             // this warp's ring: first entry, entries (warp-uniform)
+  uint64_t *const rkey = sh.ring_key[w];
+  uint32_t *const rat = sh.ring_at[w];
+  bool more = rows > 0;
+  while (more) {
+    unsigned long long g_after = 0;
+    if (threadIdx.x == 0) g_after = atomicAdd(a.tile_counter, 1ull);
+    uint64_t k[kPbKeysPerThread], v[kPbKeysPerThread];
+    uint32_t p[kPbKeysPerThread];
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      k[j] = kn[j];
+      p[j] = home_slot32(k[j], mask);
+    }
+    // ---- the ONE load phase of the iteration: the tile's home slots (linear_probing_ht.cpp:45-57) ...
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j)
+      v[j] = (uint32_t) (j * kPbThreads) + threadIdx.x < rows ? ld_table_u64<MODE>(elem_ptr_u64(a.slots, p[j]), pol) : kEmptyU;
+    // ... one pending probe sequence per lane (LPScanStructure::Next's advance, linear_probing_ht.cpp:101-109, a sector at a time) ...
+    const uint32_t npop = rn < 32u ? rn : 32u;
+    const bool popped = lane < npop;
+    uint64_t tkey = 0;
+    uint32_t tat = 0;
+    if (popped) {
+      tkey = rkey[(rhead + lane) & (kRingCap - 1)];
+      tat = rat[(rhead + lane) & (kRingCap - 1)];
+    }
+    rhead = (rhead + npop) & (kRingCap - 1);
+    rn -= npop;
+    uint64_t x[4] = {0, 0, 0, 0};
+    if (popped) ld_table_sector<MODE>(a.slots, tat & ~3u, pol, x);
+    // ... and the next tile's keys
+    lean_load_keys<MODE>(a, pol, noff, nrows, kn);
+    __syncwarp();  // every lane holds its popped entry: the ring slots may be rewritten
+    // ---- resolve the popped entries
+    bool tmatch = false, tcont = false;
+    if (popped) {
+      unsigned eq = 0, stop = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        eq |= x[i] == tkey ? (1u << i) : 0u;
+        stop |= (x[i] == tkey || x[i] == kEmptyU) ? (1u << i) : 0u;
+      }
+      stop &= 0xFu << (tat & 3u);  // slots before `tat` were examined earlier
+      if (stop)
+        tmatch = (eq & stop & (0u - stop)) != 0u;  // the first slot that ends the walk: the key, or an empty slot
+      else
+        tcont = true;
+    }
+    {
+      const unsigned bc = __ballot_sync(0xffffffffu, tcont);
+      if (tcont) {
+        const uint32_t at = (rhead + rn + __popc(bc & lt)) & (kRingCap - 1);
+        rkey[at] = tkey;
+        rat[at] = ((tat & ~3u) + 4u) & mask;
+      }
+      rn += __popc(bc);
+    }
+    // ---- home slots: match, miss, or a pending probe sequence
+    unsigned um = 0, mm = 0;
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      const bool hit = v[j] == k[j];
+      mm |= hit ? (1u << j) : 0u;
+      um |= (!hit && v[j] != kEmptyU) ? (1u << j) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      const bool u = (um & (1u << j)) != 0u;
+      const unsigned bu = __ballot_sync(0xffffffffu, u);
+      if (u) {
+        const uint32_t slot = rn + __popc(bu & lt);
+        if (slot < (uint32_t) kRingCap) {
+          const uint32_t at = (rhead + slot) & (kRingCap - 1);
+          rkey[at] = k[j];
+          rat[at] = (p[j] + 1u) & mask;
+        } else {
+          // ring full (adversarial key set): walk this key to the end right here
+          uint32_t at = (p[j] + 1u) & mask;
+          for (;;) {
+            const uint64_t y = ld_table_u64<MODE>(elem_ptr_u64(a.slots, at), pol);
+            if (y == k[j]) {
+              mm |= 1u << j;
+              break;
+            }
+            if (y == kEmptyU) break;
+            at = (at + 1u) & mask;
+          }
+        }
+      }
+      const uint32_t added = __popc(bu);
+      rn = rn + added < (uint32_t) kRingCap ? rn + added : (uint32_t) kRingCap;
+    }
+    // ---- compaction, decoupled from the global round trip (see probe_unique_kernel)
+    unsigned bal[kPbKeysPerThread];
+    uint32_t wtotal = 0;
+#pragma unroll
+    for (int j = 0; j < kPbKeysPerThread; ++j) {
+      bal[j] = __ballot_sync(0xffffffffu, (mm & (1u << j)) != 0u);
+      wtotal += __popc(bal[j]);
+    }
+    const unsigned btail = __ballot_sync(0xffffffffu, tmatch);
+    const uint32_t home_total = wtotal;
+    wtotal += __popc(btail);
+    if (lane == 0) sh.cnt[par][w] = wtotal;
+    if (threadIdx.x == 0) {
+      lean_tile_t(a, sh, g_after, sh.off[par], sh.rows[par]);
+      sh.base[par] = pending;  // output base of the PREVIOUS iteration (reserved one iteration ago)
+    }
+    const int any_pending = __syncthreads_or(rn > 0u);
+    uint32_t woff = 0, total = 0;
+    {
+      const uint4 c0 = *reinterpret_cast<const uint4 *>(&sh.cnt[par][0]), c1 = *reinterpret_cast<const uint4 *>(&sh.cnt[par][4]);
+      const uint32_t c[kPbWarps] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int i = 0; i < kPbWarps; ++i) {
+        woff += (unsigned) i < w ? c[i] : 0u;
+        total += c[i];
+      }
+    }
+    lean_flush<MODE, OUT>(a, pol, sh.stage[w], sh.base[par] + prev_woff, prev_cnt, outsel, lane);
+    __syncwarp();
+    if (OUT != 0) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) {
+        if (mm & (1u << j)) {
+          ksum += k[j];
+          sh.stage[w][run + __popc(bal[j] & lt)] = k[j];
+        }
+        run += __popc(bal[j]);
+      }
+      if (tmatch) {
+        ksum += tkey;
+        sh.stage[w][home_total + __popc(btail & lt)] = tkey;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPbKeysPerThread; ++j) ksum += (mm & (1u << j)) ? k[j] : 0ull;
+      ksum += tmatch ? tkey : 0ull;
+    }
+    __syncwarp();  // parked rows are visible to the flushing lanes
+    if (threadIdx.x == 0) pending = total ? atomicAdd((unsigned long long *) &a.res->n_matches, (unsigned long long) total) : 0ull;
+    prev_woff = woff;
+    prev_cnt = wtotal;
+    off = noff;
+    rows = nrows;
+    noff = sh.off[par];
+    nrows = sh.rows[par];
+    par ^= 1u;
+    more = rows > 0 || any_pending != 0;  // no tile left: keep iterating until every warp's ring has drained
+  }
+  // flush the rows parked by the last iteration
+  if (threadIdx.x == 0) sh.base[par] = pending;
+  __syncthreads();
+  lean_flush<MODE, OUT>(a, pol, sh.stage[w], sh.base[par] + prev_woff, prev_cnt, outsel, lane);
+  ksum = warp_sum_u64(ksum);
+  if (lane == 0 && ksum) {
+    atomicAdd((unsigned long long *) &a.res->key_sum, (unsigned long long) ksum);
+    atomicAdd((unsigned long long *) &a.res->payload_sum, (unsigned long long) ksum);  // payload == matched build key == probe key
+  }
+}
+
 // region_flag (optional): partition overrun flag of an incremental probe -> overflow bit 1
 __global__ void probe_finish_kernel(cc_probe_result *res, size_t cap, const int *region_flag = nullptr) {
   if (threadIdx.x == 0 && blockIdx.x == 0) res->overflow = (res->n_matches > cap ? 1 : 0) | ((region_flag && *region_flag) ? 2 : 0);
@@ -855,8 +1105,38 @@ static int launch_probe_lean_out(const ProbeArgs &a, cudaStream_t st) {
   return CC_OK;
 }
 
+template <int MODE, int OUT>
+static int launch_probe_lean_lp_out(const ProbeArgs &a, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_unique_lp_kernel<MODE, OUT>, kPbThreads, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  size_t ntiles = a.seg_parts ? (size_t) a.seg_parts * (size_t) (a.seg_cap / kPbTile) : (a.n + kPbTile - 1) / kPbTile;
+  size_t grid = (size_t) sm_count() * blocks_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid == 0) grid = 1;
+  probe_unique_lp_kernel<MODE, OUT><<<(unsigned) grid, kPbThreads, 0, st>>>(a);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// A/B switch for measurements: CCB_LEAN_INLINE_TAIL=1 keeps the round-1 kernel (tail walk inside the iteration) for LP tables
+static bool deferred_tail_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("CCB_LEAN_INLINE_TAIL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 template <int KIND, int MODE>
 static int launch_probe_lean(const ProbeArgs &a, cudaStream_t st) {
+  if (KIND == CC_HT_LP && deferred_tail_enabled()) {
+    if (a.out_key && a.out_payload && !a.out_rowid) return launch_probe_lean_lp_out<MODE, 3>(a, st);
+    if (!a.out_key && !a.out_payload && !a.out_rowid) return launch_probe_lean_lp_out<MODE, 0>(a, st);
+    return launch_probe_lean_lp_out<MODE, -1>(a, st);
+  }
   if (a.out_key && a.out_payload && !a.out_rowid) return launch_probe_lean_out<KIND, MODE, 3>(a, st);
   if (!a.out_key && !a.out_payload && !a.out_rowid) return launch_probe_lean_out<KIND, MODE, 0>(a, st);
   return launch_probe_lean_out<KIND, MODE, -1>(a, st);
@@ -1127,6 +1407,7 @@ int cc_probe_set_cache_mode(int mode_direct, int mode_partitioned) {
 // For a table beyond L2 every piece is scattered into the table-slice regions as it arrives (the regions fill up across
 // pieces) and the probe runs once at the end -- so the table is streamed from HBM once per batch, not once per piece, while
 // the slice partition of piece b still overlaps the exchange of piece b + 1.  For a small table every piece is probed at once.
+constexpr int kStreamMaxSegs = kMaxPeers;  // segments per piece of a small-table incremental probe (one per sender)
 struct cc_probe_stream {
   const cc_ht *ht = nullptr;
   ProbeArgs a;
@@ -1179,8 +1460,9 @@ int cc_probe_stream_begin(cc_probe_stream **out, const cc_ht *ht, size_t n_expec
     const size_t per = n_expected / h->parts;
     h->cap_rows = (per + per / 8 + 2 * (size_t) kPartTile + kPbTile - 1) / kPbTile * kPbTile;
   }
-  // control words: [0] tile counter, [2] region overrun flag, [8 ..) cursors (parts) | tile prefix (parts + 1 uint32)
-  const size_t ctl_words = 8 + 2 * (size_t) h->parts + 8;
+  // control words: [0] tile counter, [2] region overrun flag, [8 ..) cursors (parts) | tile prefix (parts + 1 uint32); a small
+  // table (parts == 0) keeps the tile prefix of a segmented piece at [8 ..): kStreamMaxSegs + 1 uint32
+  const size_t ctl_words = 8 + 2 * (size_t) h->parts + 8 + (kStreamMaxSegs + 2) / 2;
   if (e == cudaSuccess) e = cudaMallocAsync(&h->ctl, ctl_words * sizeof(unsigned long long), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(h->ctl, 0, ctl_words * sizeof(unsigned long long), st);
   if (e == cudaSuccess && h->part) e = cudaMallocAsync(&h->scratch, (size_t) h->parts * h->cap_rows * sizeof(int64_t), st);
@@ -1224,7 +1506,7 @@ int cc_probe_stream_add(cc_probe_stream *h, const int64_t *d_keys, size_t n, int
   CC_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(unsigned long long), st));
   if (seg.cap) {
     uint32_t *prefix = reinterpret_cast<uint32_t *>(h->ctl + 8);
-    CC_REQUIRE(n_segments <= 16, "a small-table incremental probe takes at most 16 segments per piece");
+    CC_REQUIRE(n_segments <= kStreamMaxSegs, "a small-table incremental probe takes at most %d segments per piece", kStreamMaxSegs);
     CC_TRY(seg_prefix_device(seg.counts, seg.segments, seg.cap, kPbTile, prefix, st));
     a.seg_prefix = prefix;
     a.seg_cursors = seg.counts;

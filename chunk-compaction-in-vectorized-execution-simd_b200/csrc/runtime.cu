@@ -13,6 +13,7 @@ namespace ccb {
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
 static int g_sm_count = 0;
+static uint64_t g_scratch_keep = ~0ull;  // release threshold of the stream-ordered scratch pool (cc_scratch_set_retention)
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -107,13 +108,37 @@ int cc_device_init(int device) {
   CC_TRY(require_device());
   g_sm_count = 0;
   sm_count();
-  // keep stream-ordered scratch (cudaMallocAsync in the partitioned probe) cached between calls
+  // keep stream-ordered scratch (cudaMallocAsync in the partitioned probe) cached between calls; cc_scratch_set_retention
+  // bounds what stays cached and cc_scratch_release hands it back (a host that shares the GPU with another allocator)
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t keep = ~0ull;
+    uint64_t keep = g_scratch_keep;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   cudaGetLastError();
+  return CC_OK;
+}
+
+int cc_scratch_set_retention(uint64_t bytes) {
+  CC_TRY(require_device());
+  g_scratch_keep = bytes;
+  int dev = 0;
+  CC_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  CC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t keep = bytes;
+  CC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  return CC_OK;
+}
+
+int cc_scratch_release(void) {
+  CC_TRY(require_device());
+  int dev = 0;
+  CC_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  CC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  CC_CUDA(cudaDeviceSynchronize());
+  CC_CUDA(cudaMemPoolTrimTo(pool, 0));
   return CC_OK;
 }
 

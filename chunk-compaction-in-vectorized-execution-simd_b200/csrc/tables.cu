@@ -335,9 +335,11 @@ static int launch_grid(size_t n, int threads, int per_sm = 8) {
   return (int) blocks;
 }
 
-static int build_lp(cc_ht *ht, const int64_t *d_keys, size_t n, int flags, cudaStream_t st) {
+// want_slots == 0: the reference's sizing rule; otherwise the caller's power of two (cc_ht_build_sized)
+static int build_lp(cc_ht *ht, const int64_t *d_keys, size_t n, int flags, cudaStream_t st, size_t want_slots = 0) {
   size_t ns = 1;
   while (ns < (n << 2)) ns <<= 1;  // linear_probing_ht.cpp:5-6
+  if (want_slots) ns = want_slots;
   ht->n_slots = ns;
   ht->mask = ns - 1;
   CC_CUDA(cudaMalloc(&ht->d_slots, ns * sizeof(uint64_t)));
@@ -372,10 +374,11 @@ static int build_lp(cc_ht *ht, const int64_t *d_keys, size_t n, int flags, cudaS
   return CC_OK;
 }
 
-static int build_chain(cc_ht *ht, const int64_t *d_keys, size_t n, cudaStream_t st) {
+static int build_chain(cc_ht *ht, const int64_t *d_keys, size_t n, cudaStream_t st, size_t want_slots = 0) {
   CC_REQUIRE(n < 0xFFFFFFFFull, "chain table supports < 2^32 keys per table (got %zu)", n);
   size_t nb = 1;
   while (nb < 2 * n) nb *= 2;  // chaining_ht.cpp:5-6
+  if (want_slots) nb = want_slots;
   ht->n_slots = nb;
   ht->mask = nb - 1;
   size_t nalloc = n ? n : 1;
@@ -446,17 +449,24 @@ using namespace ccb;
 extern "C" {
 
 int cc_ht_build(cc_ht **out, int kind, const int64_t *d_keys, size_t n, int flags, cc_stream_t s) {
+  return cc_ht_build_sized(out, kind, d_keys, n, 0, flags, s);
+}
+
+int cc_ht_build_sized(cc_ht **out, int kind, const int64_t *d_keys, size_t n, size_t n_slots, int flags, cc_stream_t s) {
   CC_REQUIRE(out, "ht is NULL");
   *out = nullptr;
   CC_TRY(require_device());
   CC_REQUIRE(kind == CC_HT_LP || kind == CC_HT_CHAIN, "unknown table kind %d", kind);
   CC_REQUIRE(n == 0 || d_keys, "d_keys is NULL");
   CC_REQUIRE(n <= (1ull << 40), "n too large");
+  CC_REQUIRE((n_slots & (n_slots - 1)) == 0, "n_slots (%zu) must be 0 or a power of two", n_slots);
+  // an LP table needs empty slots to end its probe sequences: at most half full
+  CC_REQUIRE(n_slots == 0 || kind != CC_HT_LP || n_slots >= 2 * n, "an LP table of %zu keys needs at least %zu slots (got %zu)", n, 2 * n, n_slots);
   cc_ht *ht = new cc_ht();
   ht->kind = kind;
   ht->n_keys = n;
   cudaGetDevice(&ht->device);
-  int rc = kind == CC_HT_LP ? build_lp(ht, d_keys, n, flags, as_stream(s)) : build_chain(ht, d_keys, n, as_stream(s));
+  int rc = kind == CC_HT_LP ? build_lp(ht, d_keys, n, flags, as_stream(s), n_slots) : build_chain(ht, d_keys, n, as_stream(s), n_slots);
   if (rc != CC_OK) {
     free_table(ht);
     return rc;

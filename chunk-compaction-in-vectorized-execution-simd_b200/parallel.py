@@ -56,6 +56,20 @@ def choose_plan(n_build_total: int, n_probe_total: int, world: int) -> str:
     return "broadcast" if n_build_total * 16 * world * 4 < n_probe_total * 8 else "partition"
 
 
+def table_slots(lp: bool, n_total: int, n_local: int, world: int) -> int:
+    """Slot / bucket count of one rank's table in the partitioned join: the reference's sizing rule on the GLOBAL key count
+    (LP: pow2 >= 4 n, linear_probing_ht.cpp:5-6; chain: pow2 >= 2 n, chaining_ht.cpp:5-6) divided by the (power-of-two) number
+    of ranks -- doubled while a skewed partition would push an LP table beyond half full."""
+    per_key = 4 if lp else 2
+    total = 1
+    while total < per_key * n_total:
+        total <<= 1
+    slots = max(1, total // world)
+    while lp and slots < 2 * n_local:
+        slots <<= 1
+    return slots
+
+
 class PeerExchange:
     """Fused scatter + exchange over peer memory (NVLink 5 / NVSwitch).
 
@@ -120,9 +134,14 @@ class PeerExchange:
         dist.all_gather_into_tensor(self._matrix, self._counts, group=self.group)
         m = self._matrix.view(self.world, self.world)  # m[sender][owner]
         base = m[: self.rank].sum(dim=0).contiguous()  # rows of earlier senders in each owner's buffer
-        n_recv = int(m[:, self.rank].sum().item())
-        if n_recv > self.capacity:
-            raise RuntimeError(f"receive buffer too small: {n_recv} rows > capacity {self.capacity}")
+        # EVERY rank holds the full P x P matrix, so every rank checks EVERY receive column: if any owner's buffer would
+        # overflow, all ranks raise together -- nobody stores past the end of a peer's buffer over NVLink and nobody is
+        # left alone in the barrier below
+        recv_all = m.sum(dim=0).cpu()
+        n_recv = int(recv_all[self.rank])
+        if int(recv_all.max()) > self.capacity:
+            worst = int(recv_all.argmax())
+            raise RuntimeError(f"receive buffer of rank {worst} too small: {int(recv_all[worst])} rows > capacity {self.capacity}")
         pkg._lib.check(lib.cc_partition_scatter_peers(keys.data_ptr() if n else None, n, self.log2p, base.data_ptr(),
                                                       self._cursors.data_ptr(), self.peers[b], stream))
         if reader_done is not None:
@@ -161,7 +180,7 @@ class CopyExchange:
 
     TILE = 4096  # region capacities are multiples of the partition kernel's tile
 
-    def __init__(self, pkg, max_rows: int, group=None, n_buffers: int = 3):
+    def __init__(self, pkg, max_rows: int, group=None, n_buffers: int = 3, copy_streams: int = 4):
         import ctypes as C
 
         self.pkg, self.group = pkg, group
@@ -201,7 +220,10 @@ class CopyExchange:
         self.mine = [torch.zeros(self.world, dtype=torch.int64, device=dev) for _ in range(n_buffers)]
         self.overflow = torch.zeros(n_buffers, dtype=torch.int32, device=dev)
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._copy_stream = torch.cuda.Stream()
+        # The block copies of one shuffle go out on several copy streams: one stream drives one copy engine at a time, and a
+        # single engine does not fill an NVLink 5 port (round 1: 450 GB/s effective with one stream).  Destinations are dealt
+        # round-robin, so that concurrent copies of a rank always target different peers.
+        self._copy_streams = [torch.cuda.Stream() for _ in range(max(1, min(int(copy_streams), self.world - 1)))]
         self._copied = [None] * n_buffers
         dist.barrier(group=group)
 
@@ -222,28 +244,37 @@ class CopyExchange:
         parted.record(main)
         dist.all_gather_into_tensor(self.matrix[b], self.counts[b], group=self.group)  # matrix[sender * P + owner]
         self.mine[b].copy_(self.matrix[b].view(self.world, self.world)[:, self.rank])  # rows every sender delivers to this rank
-        cs = self._copy_stream
-        cs.wait_event(parted)
+        for cs in self._copy_streams:
+            cs.wait_event(parted)
         src = self.send[b].data_ptr()
         block = self.cap * 8
-        for i in range(0 if self.world > 16 else 1, self.world):
+        for j, i in enumerate(range(0 if self.world > 16 else 1, self.world)):
             p = (self.rank + i) % self.world  # stagger the destinations so that the ranks do not all hit the same peer at once
+            cs = self._copy_streams[j % len(self._copy_streams)]
             pkg._lib.check(lib.cc_memcpy_d2d(self.peers[b][p] + self.rank * block, src + p * block, block, cs.cuda_stream))
-        done = torch.cuda.Event()
-        done.record(cs)
+        done = []
+        for cs in self._copy_streams:
+            e = torch.cuda.Event()
+            e.record(cs)
+            done.append(e)
         self._copied[b] = done
         return k
 
     def finish(self, k: int):
         """Second half of shuffle k: returns (segmented receive column, segment capacity, device counts[P])."""
         b = k % self.n_buffers
-        torch.cuda.current_stream().wait_event(self._copied[b])
+        for e in self._copied[b]:
+            torch.cuda.current_stream().wait_event(e)
         dist.all_reduce(self._token, group=self.group)  # stream-ordered barrier: every rank's copies have landed
         return self.pkg._wrap_ptr(self.local[b], self.rows, torch.int64), self.cap, self.mine[b]
 
     def check_overflow(self) -> None:
-        """Raises if any shuffle since the last check overran a region (synchronises)."""
-        bad = int(self.overflow.sum().item())
+        """Raises ON EVERY RANK if any shuffle of any rank since the last check overran a region (synchronises; collective).
+        The per-buffer flags are sticky (cc_partition_single only ORs into them), so an overrun in ANY shuffle since the
+        last check is seen, not just in the last n_buffers ones."""
+        bad_t = (self.overflow != 0).sum().to(torch.int32).reshape(1)
+        dist.all_reduce(bad_t, op=dist.ReduceOp.MAX, group=self.group)
+        bad = int(bad_t.item())
         self.overflow.zero_()
         if bad:
             raise RuntimeError("copy-engine exchange: a partition region overran (heavily skewed keys); use exchange='p2p' or 'nccl'")
@@ -263,7 +294,7 @@ class PartitionedJoin:
     """Build once, probe many times.  `pkg` is the product package (passed in to avoid a circular import)."""
 
     def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, group=None, plan: str = "partition",
-                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0, ce_probe: str = "auto"):
+                 exchange: str = "nccl", capacity_rows: int = 0, peer_blocks: int = 0, ce_probe: str = "auto", copy_streams: int = 4):
         """plan: "partition" (hash-partition both sides) or "broadcast" (replicate the build side).
         exchange: "nccl" (scatter locally, then all_to_all_single), "p2p" (PeerExchange: the scatter kernel
         writes into the owners' buffers over NVLink) or "ce" (CopyExchange: single-pass partition + copy-engine block
@@ -282,8 +313,18 @@ class PartitionedJoin:
         self.log2p = log2_exact(self.world)
         self.plan = plan
         self.ce_probe = ce_probe if ce_probe != "auto" else ("stream" if self.world <= 2 else "batch")
+        import time
+
+        def lap(name, t0):  # wall-clock phases of the (untimed) build, reported by bench.py as build_phases
+            torch.cuda.synchronize()
+            self.build_phases[name] = time.perf_counter() - t0
+            return time.perf_counter()
+
+        self.build_phases = {}
+        t0 = time.perf_counter()
         self.peer = PeerExchange(pkg, capacity_rows, group, peer_blocks=peer_blocks) if (exchange == "p2p" and plan == "partition") else None
-        self.copier = CopyExchange(pkg, capacity_rows, group) if (exchange == "ce" and plan == "partition") else None
+        self.copier = CopyExchange(pkg, capacity_rows, group, copy_streams=copy_streams) if (exchange == "ce" and plan == "partition") else None
+        t0 = lap("exchange_setup_s", t0)
         T = pkg.LPHashTable if kind == pkg.CC_HT_LP else pkg.HashTable
         if plan == "broadcast":
             n_local = torch.tensor([local_build_keys.numel()], dtype=torch.int64, device=local_build_keys.device)
@@ -299,10 +340,20 @@ class PartitionedJoin:
             dist.all_gather(gathered, padded, group=group)
             keys = torch.cat([g[:s] for g, s in zip(gathered, sizes)])
             del parts
+            n_slots = 0  # every rank holds the whole build side: the reference's sizing rule applies as is
         else:
             keys = self.shuffle(local_build_keys)
+            # Size the local table from the GLOBAL key count: the reference's rule (pow2 >= 4n for LP, linear_probing_ht.cpp:5-6;
+            # pow2 >= 2n for chains, chaining_ht.cpp:5-6) applied to the whole build side, divided by the number of ranks.
+            # Applied to the LOCAL count it doubles the table whenever a hash partition lands a hair above n_total / P
+            # (round 1: 134 224 497 keys > 2^27 by 0.005 % -> 2^30 slots = 8 GiB at load factor 0.125 on every rank).
+            n_total = torch.tensor([local_build_keys.numel()], dtype=torch.int64, device=local_build_keys.device)
+            dist.all_reduce(n_total, group=group)
+            n_slots = table_slots(kind == pkg.CC_HT_LP, int(n_total.item()), keys.numel(), self.world)
+        t0 = lap("build_exchange_s", t0)
         self.n_build_local = keys.numel()
-        self.table = T(keys=keys)
+        self.table = T(keys=keys, n_slots=n_slots)
+        lap("table_build_s", t0)
 
     def shuffle(self, keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Hash-partition `keys` and exchange: returns the rows this rank owns."""
@@ -343,7 +394,7 @@ class PartitionedJoin:
             done.record(main)
             self._probe_done[k] = done
 
-    def _probe_pipelined_ce(self, local_probe_keys, n_sub, out_key, out_payload, results) -> None:
+    def _probe_pipelined_ce(self, local_probe_keys, n_sub, out_key, out_payload, results, ready=None, landed=None) -> None:
         """Copy-engine variant: everything that needs SMs is enqueued on the CURRENT stream in the order
         P(0) P(1) B(0) S(0) P(2) B(1) S(1) ... B(n-1) S(n-1) PROBE  (P = owner partition of a sub-batch, B = barrier, S = scatter
         of the received sub-batch into the table-slice regions of ONE incremental probe, cc_probe_stream_*) while the block
@@ -355,17 +406,26 @@ class PartitionedJoin:
         import os
         cx = self.copier
         chunks = list(local_probe_keys.chunk(n_sub))
+        main = torch.cuda.current_stream()
+
+        def start(b):  # ready[b] (optional): event after which chunk b holds its keys (the H2D copy of probe_host)
+            if ready is not None:
+                main.wait_event(ready[b])
+            return cx.start(chunks[b])
+
         if self.ce_probe == "batch":
             # P(0) P(1) B(0) L(0) P(2) B(1) L(1) ...  with L = slice partition + probe of ONE received sub-batch: the block
             # copies C(b + 1) run underneath L(b).  results[b] / slice b of the output columns belong to sub-batch b.
             cap = out_key.numel() // n_sub
-            pending = [cx.start(chunks[0])]
+            pending = [start(0)]
             for b in range(len(chunks)):
                 if b + 1 < len(chunks):
-                    pending.append(cx.start(chunks[b + 1]))
+                    pending.append(start(b + 1))
                 recv, seg_cap, counts = cx.finish(pending[b])
                 self.table.probe_batch_segmented(recv, self.world, seg_cap, counts, capacity=cap, out_key=out_key[b * cap:(b + 1) * cap],
                                                  out_payload=out_payload[b * cap:(b + 1) * cap], result=results[b], sync=False)
+                if landed is not None:
+                    landed(b)  # sub-batch b's rows and counter are final once the work enqueued so far has run
             return
         trace = [] if os.environ.get("CCB_CE_TRACE") else None  # evidence switch: CUDA-event timeline of one call (synchronises)
 
@@ -379,11 +439,11 @@ class PartitionedJoin:
         n_local = local_probe_keys.numel()
         stream = self.table.probe_stream(n_local + n_local // 16 + (1 << 16), capacity=out_key.numel(), out_key=out_key, out_payload=out_payload,
                                          result=results[0])
-        pending = [cx.start(chunks[0])]
+        pending = [start(0)]
         mark("P0")
         for b in range(len(chunks)):
             if b + 1 < len(chunks):
-                pending.append(cx.start(chunks[b + 1]))
+                pending.append(start(b + 1))
                 mark(f"P{b + 1}")
             recv, seg_cap, counts = cx.finish(pending[b])
             mark(f"B{b}")
@@ -394,6 +454,79 @@ class PartitionedJoin:
         if trace is not None and self.rank == 0:
             torch.cuda.synchronize()
             print("ce timeline (ms since begin): " + "  ".join(f"{n}={trace[0][1].elapsed_time(e):.2f}" for n, e in trace[1:]), flush=True)
+
+    def probe_host(self, h_keys: torch.Tensor, h_out_key: torch.Tensor, h_out_payload: torch.Tensor, n_sub: int = 4) -> int:
+        """End to end with HOST buffers (pinned int64 tensors): this rank's probe keys travel host -> device, through partition +
+        exchange + probe, and the result rows this rank ends up owning travel back.  Returns their number (rows [0, n) of
+        h_out_key / h_out_payload).  Everything overlaps: the H2D copies run chunk by chunk on their own stream ahead of the
+        owner partitions, and with the copy-engine exchange in "batch" mode the rows of sub-batch b go back to the host (on a
+        third stream) as soon as its 32-byte result record has landed in pinned memory, while sub-batch b + 1 is still being
+        exchanged and probed -- the host never waits for more than one small record per sub-batch."""
+        n = h_keys.numel()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ws = getattr(self, "_host_ws", None)
+        cap = n + n // 8 + (1 << 16)
+        cap -= cap % n_sub
+        if ws is None or ws["n"] < n or ws["n_sub"] != n_sub:
+            ws = {"n": n, "n_sub": n_sub, "dk": torch.empty(n, dtype=torch.int64, device=dev),
+                  "ok": torch.empty(cap, dtype=torch.int64, device=dev), "op": torch.empty(cap, dtype=torch.int64, device=dev),
+                  "res": torch.zeros((n_sub, 4), dtype=torch.int64, device=dev),
+                  "hres": torch.zeros((n_sub, 4), dtype=torch.int64).pin_memory(),
+                  "s_in": torch.cuda.Stream(), "s_out": torch.cuda.Stream(), "cap": cap}
+            self._host_ws = ws
+        dk, ok, op, res, hres, cap = ws["dk"][:n], ws["ok"], ws["op"], ws["res"], ws["hres"], ws["cap"]
+        main = torch.cuda.current_stream()
+        s_in, s_out = ws["s_in"], ws["s_out"]
+        s_in.wait_stream(main)
+        ready = []
+        with torch.cuda.stream(s_in):
+            for dchunk, hchunk in zip(dk.chunk(n_sub), h_keys.chunk(n_sub)):
+                dchunk.copy_(hchunk, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ready.append(e)
+        hcap = min(h_out_key.numel(), h_out_payload.numel())
+        res.zero_()
+        batch = self.copier is not None and self.ce_probe == "batch" and self.plan == "partition"
+        if batch:
+            done = []
+
+            def landed(b):
+                hres[b].copy_(res[b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(main)
+                done.append(e)
+
+            self._probe_pipelined_ce(dk, n_sub, ok, op, res, ready=ready, landed=landed)
+            capb, off = cap // n_sub, 0
+            for b, e in enumerate(done):
+                e.synchronize()  # the 32-byte record of sub-batch b is in pinned memory
+                m = min(int(hres[b, 0]), capb, hcap - off)
+                if m > 0:
+                    s_out.wait_event(e)
+                    with torch.cuda.stream(s_out):
+                        h_out_key[off:off + m].copy_(ok[b * capb:b * capb + m], non_blocking=True)
+                        h_out_payload[off:off + m].copy_(op[b * capb:b * capb + m], non_blocking=True)
+                off += max(m, 0)
+            s_out.synchronize()
+            return off
+        # one dense run of rows: stream-mode copy-engine pipeline, the fused peer scatter, NCCL all-to-all or the broadcast plan
+        if self.copier is not None and self.plan == "partition":
+            self._probe_pipelined_ce(dk, n_sub, ok, op, res, ready=ready)
+        else:
+            main.wait_event(ready[-1])
+            if self.peer is not None and self.plan == "partition":
+                self.probe_pipelined(dk, 1, ok, op, res[:1])
+            else:
+                self.probe(dk, capacity=cap, out_key=ok, out_payload=op, result=res[0], sync=False)
+        hres.copy_(res, non_blocking=True)
+        main.synchronize()
+        m = min(int(hres[0, 0]), cap, hcap)
+        if m > 0:
+            h_out_key[:m].copy_(ok[:m], non_blocking=True)
+            h_out_payload[:m].copy_(op[:m], non_blocking=True)
+            main.synchronize()
+        return max(m, 0)
 
     def probe(self, local_probe_keys: torch.Tensor, **kw) -> dict:
         """One probe pass: (partition + all-to-all unless broadcast plan) + local batch probe."""

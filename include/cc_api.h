@@ -89,6 +89,12 @@ int cc_memset(void *d_dst, int byte, size_t bytes, cc_stream_t stream);
 int cc_stream_create(cc_stream_t *stream);
 int cc_stream_destroy(cc_stream_t stream);
 int cc_stream_sync(cc_stream_t stream);
+/* Stream-ordered scratch (the partitioned probe's key regions, cudaMallocAsync) is cached in the device's default memory
+ * pool between calls -- about 18 GiB after one 2^31-key probe, invisible to any other allocator in the process.
+ * cc_scratch_set_retention bounds what stays cached once the work has drained (default: everything), cc_scratch_release
+ * synchronises the device and hands all of it back.                                                                    */
+int cc_scratch_set_retention(uint64_t bytes);
+int cc_scratch_release(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t cc_launch_count(void);
 
@@ -117,6 +123,11 @@ typedef struct {
  * own keys; see cc_ht_build_reference).  Key -1 is rejected for LP tables
  * (empty-slot sentinel, linear_probing_ht.cpp:7).                             */
 int cc_ht_build(cc_ht **ht, int kind, const int64_t *d_keys, size_t n, int flags, cc_stream_t stream);
+/* The same with the slot / bucket count chosen by the caller (a power of two; 0 = the reference's rule above).  The
+ * partitioned multi-GPU join sizes every rank's table from the GLOBAL key count (pow2 >= 4 n_total, divided by the number
+ * of ranks) so that a hash partition that is 0.005 % above n_total / P does not double the table
+ * (linear_probing_ht.cpp:5-6 sizes for one table; the result multiset does not depend on the slot count).  LP: n_slots >= 2n. */
+int cc_ht_build_sized(cc_ht **ht, int kind, const int64_t *d_keys, size_t n, size_t n_slots, int flags, cc_stream_t stream);
 /* exact equivalent of `HashTable(n_rhs_tuples, chunk_factor)` /
  * `LPHashTable(n_rhs_tuples, chunk_factor)` (chaining_ht.h:88, linear_probing_ht.h:58) */
 int cc_ht_build_reference(cc_ht **ht, int kind, size_t n_rhs_tuples, size_t chunk_factor, cc_stream_t stream);
@@ -367,7 +378,9 @@ int cc_partition_scatter(const int64_t *d_keys, size_t n, int log2_parts, const 
                          uint64_t *d_cursors, int64_t *d_out, cc_stream_t stream);
 /* Single-pass variant (no histogram, no host round trip): partition p is scattered into the fixed region
  * d_out[p * region_capacity ...]; d_counts[p] = its rows; *d_overflow != 0 if a region overran (heavily skewed keys: the
- * output is then unusable and the two-pass pair above must be used).  Send side of the copy-engine exchange: region p is
+ * output is then unusable and the two-pass pair above must be used).  *d_overflow is STICKY: the call only ever ORs into
+ * it and never clears it, so one flag can watch over many calls -- the caller zeroes it (before the first call, and after
+ * every look at it).  Send side of the copy-engine exchange: region p is
  * then copied into peer p's receive buffer (cc_ipc_open) with cc_memcpy_d2d, which a copy engine executes over NVLink
  * without occupying an SM.  self_part >= 0 (needs <= 16 partitions): that one partition is written to d_self_out at the
  * same region offset instead -- the rows a rank keeps go straight into its own receive buffer.                                                                                              */

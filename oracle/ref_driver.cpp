@@ -18,8 +18,9 @@
 //         same pipeline over an explicit row-major int64 LHS file; kind 0 LP, 1 chain
 //   nextdump kind n cf block keys.bin nkeys inone out.bin
 //         per-Next golden records of the chunk-granular protocol
-//   micro kind variant n cf block keys.bin nkeys procs
-//         times one micro-bench variant (simd_micro_bench.cpp:83-361 loop shape)
+//   micro kind variant n cf block keys.bin nkeys procs [share [reps]]
+//         times one micro-bench variant (simd_micro_bench.cpp:83-361 loop shape); share = 1: one table built before the
+//         fork and shared by the workers; reps: timed repetitions over the same table ("seconds" = the best one)
 //         variant: 0 scalar Probe+Next, 1 SIMD Probe+Next, 2 scalar InOneNext, 3 SIMD InOneNext
 //         procs > 1 forks that many workers over disjoint key ranges sharing the
 //         read-only table (the reference itself is single-threaded; its
@@ -255,20 +256,32 @@ uint64_t MicroLoop(HT &table, const int64_t *keys, size_t nkeys, int variant) {
 }
 
 template <class HT>
-int Micro(size_t n, size_t cf, const std::vector<int64_t> &keys, int variant, int procs) {
-  // procs > 1: fork FIRST, every worker builds its own private table (children of a process that
-  // already holds the table run ~3x slower per key here: copy-on-write heap traffic), then all
-  // workers start together on disjoint key ranges; throughput = all keys / slowest worker.
+int Micro(size_t n, size_t cf, const std::vector<int64_t> &keys, int variant, int procs, int share, int reps) {
+  // procs > 1: workers are forked processes (the reference is single-threaded and its CycleProfiler singleton is not
+  // thread-safe, profiler.h:262-290) over disjoint key ranges; all of them start every repetition together and a
+  // repetition's time is its slowest worker's.  share == 0: fork FIRST, every worker builds its own private table;
+  // share == 1: ONE table is built before the fork and shared copy-on-write (read-only afterwards) -- the only way a
+  // 2^28-key table (8 GiB) fits beside 16 workers.  The table is built once, then `reps` timed repetitions run.
+  if (reps < 1) reps = 1;
+  std::vector<double> rep_secs(reps, 0.0);
   uint64_t total = 0;
-  double secs = 0, build_s = 0;
+  double build_s = 0;
   if (procs <= 1) {
     auto b0 = std::chrono::steady_clock::now();
     HT table(n, cf);
     build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
-    auto t0 = std::chrono::steady_clock::now();
-    total = MicroLoop(table, keys.data(), keys.size(), variant);
-    secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int r = 0; r < reps; ++r) {
+      auto t0 = std::chrono::steady_clock::now();
+      total = MicroLoop(table, keys.data(), keys.size(), variant);
+      rep_secs[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
   } else {
+    std::unique_ptr<HT> shared;
+    if (share) {
+      auto b0 = std::chrono::steady_clock::now();
+      shared = std::make_unique<HT>(n, cf);
+      build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+    }
     std::vector<int> res_fd(procs), go_fd(procs), ready_fd(procs);
     std::vector<pid_t> pids(procs);
     size_t per = (keys.size() / procs / kBlockSize) * kBlockSize;
@@ -282,16 +295,21 @@ int Micro(size_t n, size_t cf, const std::vector<int64_t> &keys, int variant, in
         close(go[1]);
         close(ready[0]);
         auto b0 = std::chrono::steady_clock::now();
-        HT table(n, cf);
+        std::unique_ptr<HT> own;
+        if (!share) own = std::make_unique<HT>(n, cf);
+        HT &table = share ? *shared : *own;
         double bs = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
         char c = 1;
-        if (write(ready[1], &c, 1) != 1 || read(go[0], &c, 1) != 1) _exit(4);
+        if (write(ready[1], &c, 1) != 1) _exit(4);
         size_t lo = std::min(keys.size(), (size_t) p * per);
         size_t hi = p == procs - 1 ? keys.size() : std::min(keys.size(), lo + per);
-        auto c0 = std::chrono::steady_clock::now();
-        uint64_t r = MicroLoop(table, keys.data() + lo, hi - lo, variant);
-        double out[3] = {std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count(), (double) r, bs};
-        if (write(res[1], out, sizeof(out)) != (ssize_t) sizeof(out)) _exit(4);
+        for (int r = 0; r < reps; ++r) {
+          if (read(go[0], &c, 1) != 1) _exit(4);
+          auto c0 = std::chrono::steady_clock::now();
+          uint64_t cnt = MicroLoop(table, keys.data() + lo, hi - lo, variant);
+          double out[3] = {std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count(), (double) cnt, bs};
+          if (write(res[1], out, sizeof(out)) != (ssize_t) sizeof(out)) _exit(4);
+        }
         _exit(0);
       }
       close(res[1]);
@@ -305,20 +323,29 @@ int Micro(size_t n, size_t cf, const std::vector<int64_t> &keys, int variant, in
     char c = 0;
     for (int p = 0; p < procs; ++p)
       if (read(ready_fd[p], &c, 1) != 1) return 5;
-    for (int p = 0; p < procs; ++p)
-      if (write(go_fd[p], &c, 1) != 1) return 5;
+    for (int r = 0; r < reps; ++r) {
+      for (int p = 0; p < procs; ++p)
+        if (write(go_fd[p], &c, 1) != 1) return 5;
+      total = 0;
+      for (int p = 0; p < procs; ++p) {
+        double out[3] = {0, 0, 0};
+        if (read(res_fd[p], out, sizeof(out)) != (ssize_t) sizeof(out)) return 5;
+        rep_secs[r] = std::max(rep_secs[r], out[0]);
+        total += (uint64_t) out[1];
+        if (!share) build_s = std::max(build_s, out[2]);
+      }
+    }
     for (int p = 0; p < procs; ++p) {
-      double out[3] = {0, 0, 0};
-      if (read(res_fd[p], out, sizeof(out)) != (ssize_t) sizeof(out)) return 5;
-      secs = std::max(secs, out[0]);
-      total += (uint64_t) out[1];
-      build_s = std::max(build_s, out[2]);
       int st;
       waitpid(pids[p], &st, 0);
     }
   }
-  printf("{\"n_tuples\": %llu, \"seconds\": %.6f, \"build_seconds\": %.3f, \"probe_keys\": %zu, \"procs\": %d, \"variant\": %d}\n",
-         (unsigned long long) total, secs, build_s, keys.size(), procs > 1 ? procs : 1, variant);
+  double best = rep_secs[0];
+  for (double x : rep_secs) best = std::min(best, x);
+  printf("{\"n_tuples\": %llu, \"seconds\": %.6f, \"build_seconds\": %.3f, \"probe_keys\": %zu, \"procs\": %d, \"variant\": %d, \"shared_table\": %d, \"rep_seconds\": [",
+         (unsigned long long) total, best, build_s, keys.size(), procs > 1 ? procs : 1, variant, share ? 1 : 0);
+  for (int r = 0; r < reps; ++r) printf("%s%.6f", r ? ", " : "", rep_secs[r]);
+  printf("]}\n");
   return 0;
 }
 
@@ -367,7 +394,9 @@ int main(int argc, char **argv) {
     kBlockSize = atol(argv[6]);
     auto keys = ReadFile(argv[7], atol(argv[8]));
     int procs = atoi(argv[9]);
-    return kind == 0 ? Micro<LPHashTable>(n, cf, keys, variant, procs) : Micro<HashTable>(n, cf, keys, variant, procs);
+    int share = argc > 10 ? atoi(argv[10]) : 0, reps = argc > 11 ? atoi(argv[11]) : 1;
+    return kind == 0 ? Micro<LPHashTable>(n, cf, keys, variant, procs, share, reps)
+                     : Micro<HashTable>(n, cf, keys, variant, procs, share, reps);
   }
   if (cmd == "bandit" && argc >= 3) {
     size_t steps = atol(argv[2]);

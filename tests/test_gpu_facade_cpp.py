@@ -58,8 +58,6 @@ def test_cpp_driver_payload_mode(ccb, table):
 MICRO = os.path.join(ROOT, PKG_NAME, "host", "micro_bench_main")
 
 
-@pytest.mark.skip(reason="micro_bench_main.cpp was written after round 1's GPU budget was spent: it compiles, links and refuses to run "
-                         "without a GPU, but has not run on a B200 yet -- round 2 removes this marker after the first run")
 @pytest.mark.parametrize("scale,hit,cf", [(3, 2, 1), (3, 1, 4), (0, 4, 8)])
 def test_cpp_micro_bench_driver(ccb, scale, hit, cf):
     """the ported simd_micro_bench driver: every variant (chunk protocol Next / InOneNext and the fused batch probe, both

@@ -297,6 +297,37 @@ def test_probe_batch_negative_and_extreme_keys(ccb, strategy):
         assert np.array_equal(G.sort_rows(got), G.sort_rows(want["tuples"]))
 
 
+def test_probe_batch_clustered_keys(ccb, strategy):
+    """Adversarial LP table for the deferred tail walk of probe_unique_lp_kernel: 2000 unique build keys whose home slots all
+    fall into 64 of the 8192 slots, i.e. ONE cluster of ~2000 consecutive occupied slots.  Nearly every probe key finds another
+    key in its home slot (all 128 keys of a warp are pending at once: the per-warp ring overflows and the excess is walked on
+    the spot), probe sequences run over hundreds of sectors (entries circulate through the ring for hundreds of iterations), and
+    the key column ends long before the rings have drained (tile-less drain iterations).  Misses walk to the end of the cluster."""
+    n = 2000
+    n_slots = 8192
+    cand = np.arange(1, 4_000_000, dtype=np.int64)
+    home = O.murmurhash64(cand.view(np.uint64)) & np.uint64(n_slots - 1)
+    cand = cand[home < 64]
+    assert cand.size > 3 * n
+    bk = cand[:n].copy()
+    absent = cand[n:3 * n]
+    rng = np.random.Generator(np.random.PCG64(5))
+    for nprobe in (100, 5000, 200000):
+        probe = np.concatenate([rng.choice(bk, size=nprobe), rng.choice(absent, size=nprobe // 2), rng.integers(0, 1 << 40, size=nprobe // 4, dtype=np.int64)])
+        rng.shuffle(probe)
+        gtab = ccb.LPHashTable(keys=bk)
+        assert gtab.info().n_slots == n_slots and gtab.info().has_duplicates == 0
+        want = O.pipeline([O.OracleLP(bk)], probe.reshape(-1, 1), 2048, collect=True)
+        r = gtab.probe_batch(dev(probe), capacity=probe.size)
+        m = r["n_matches"]
+        assert m == want["n_tuples"] and r["overflow"] == 0
+        assert r["key_sum"] == u64sum(want["tuples"][:, 0]) and r["payload_sum"] == u64sum(want["tuples"][:, 2])
+        got = np.stack([r["out_key"][:m].cpu().numpy(), np.zeros(m, dtype=np.int64), r["out_payload"][:m].cpu().numpy()], axis=1)
+        assert np.array_equal(G.sort_rows(got), G.sort_rows(want["tuples"]))
+        r2 = gtab.probe_batch(dev(probe), materialize=False)
+        assert (r2["n_matches"], r2["key_sum"]) == (m, r["key_sum"])
+
+
 def test_probe_batch_microbench_known_answer(ccb):
     """simd_micro_bench --scale 3 --hit-frequency 2: #tuples == 67114250 over 2^27 glibc rand() keys."""
     keys = O.gen_keys_rand(1 << 27, 1024 * 2 - 1)

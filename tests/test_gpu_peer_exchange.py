@@ -211,6 +211,10 @@ def test_partition_single_regions(ccb):
     same = torch.full((n,), 42, dtype=torch.int64, device="cuda")  # every key in one partition: the region must overrun
     _, _, flag = ccb.partition_single(same, log2p, cap)
     assert int(flag.item()) != 0
+    # the flag is sticky: a later, well-behaved call on the same flag must not erase the report (one flag watches over
+    # all shuffles of a step in the copy-engine exchange)
+    _, counts2, flag = ccb.partition_single(keys, log2p, cap, overflow=flag)
+    assert int(flag.item()) != 0 and int(counts2.sum().item()) == n
 
 
 @pytest.mark.parametrize("log2p", [1, 2, 3, 4, 5])
