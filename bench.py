@@ -201,7 +201,9 @@ def run_reference_arm(args):
     return 0
 
 
-EXCHANGES = {"ce": "probe side: single-pass owner partition + copy-engine block copies over NVLink underneath the probe of the previous sub-batch",
+EXCHANGES = {"cabi": "everything behind the C ABI (cc_pjoin_*): single-pass owner partition + copy-engine block copies into IPC-mapped peer memory over NVLink, "
+                     "device-side ready / consumed flags, no collective on the data path",
+             "ce": "probe side: single-pass owner partition + copy-engine block copies over NVLink underneath the probe of the previous sub-batch",
              "p2p": "scatter kernel stores into peer memory over NVLink", "nccl": "NCCL all-to-all"}
 
 
@@ -218,6 +220,7 @@ def workload_config(args) -> dict:
                         f"dense key+payload output (results stay sharded)",
             "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "exchange": args.exchange, "sub_batches": args.sub_batches,
             "ce_probe": (args.ce_probe if args.ce_probe != "auto" else ("stream" if args.gpus <= 2 else "batch")) if args.exchange == "ce" else None,
+            "copy_streams": args.copy_streams if args.exchange == "ce" else (4 if args.exchange == "cabi" else None),
             "l2_policy": "inputs far exceed L2; no flush needed"}
 
 
@@ -316,7 +319,7 @@ def main() -> int:
                          "or stream up to 2 GPUs and batch beyond (auto)")
     ap.add_argument("--copy-streams", type=int, default=4, help="N>1 with --exchange ce: copy streams the block copies of one shuffle are dealt over")
     ap.add_argument("--no-chain", action="store_true", help="N=1: skip the C3 join-chain sub-record")
-    ap.add_argument("--exchange", default="ce", choices=["ce", "p2p", "nccl"],
+    ap.add_argument("--exchange", default="ce", choices=["ce", "cabi", "p2p", "nccl"],
                     help="N>1: copy-engine block copies under the probe (default), fused peer-memory scatter kernel, or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "ours":
@@ -326,7 +329,7 @@ def main() -> int:
     if args.log2_probe is None:
         args.log2_probe = 31 if args.gpus == 1 else 30
     if args.sub_batches is None:
-        args.sub_batches = 4 if (args.gpus > 1 and args.exchange == "ce") else 1
+        args.sub_batches = 4 if (args.gpus > 1 and args.exchange in ("ce", "cabi")) else 1
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -366,13 +369,17 @@ def main() -> int:
         key_space = n_build * world
         local_build = torch.arange(rank * n_build, (rank + 1) * n_build, dtype=torch.int64, device=dev)  # keys 0..N*nb-1, cf=1
         cap_rows = -(-n_probe // args.sub_batches) if args.exchange == "ce" else int(n_probe * 1.05) + (1 << 20)
-        join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
-                                   capacity_rows=cap_rows, peer_blocks=args.peer_blocks, ce_probe=args.ce_probe, copy_streams=args.copy_streams)
-        table = join.table
+        if args.exchange == "cabi":
+            join = par.CPartitionedJoin(pkg, pkg.CC_HT_LP, local_build, n_probe, n_sub=args.sub_batches)
+            table = None
+        else:
+            join = par.PartitionedJoin(pkg, pkg.CC_HT_LP, local_build, plan="partition", exchange=args.exchange,
+                                       capacity_rows=cap_rows, peer_blocks=args.peer_blocks, ce_probe=args.ce_probe, copy_streams=args.copy_streams)
+            table = join.table
         del local_build
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
-    info = table.info()
+    info = table.info() if table is not None else join.table_info()
 
     # ---- probe side resident in HBM
     keys = pkg.gen_keys_counter(n_probe, 2, key_space - 1, first=rank * n_probe)
@@ -380,7 +387,7 @@ def main() -> int:
     cap -= cap % max(1, args.sub_batches)
     out_key = torch.empty(cap, dtype=torch.int64, device=dev)
     out_payload = torch.empty(cap, dtype=torch.int64, device=dev)
-    n_sub = args.sub_batches if (distributed and args.exchange in ("p2p", "ce")) else 1
+    n_sub = args.sub_batches if (distributed and args.exchange in ("p2p", "ce")) else 1  # result records: "cabi" accumulates into ONE
     result = torch.zeros((n_sub, 4), dtype=torch.int64, device=dev)
     recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if (distributed and args.exchange == "nccl") else None
     expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
@@ -389,6 +396,8 @@ def main() -> int:
         k = keys if k is None else k
         if not distributed:
             return table.probe_batch(k, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
+        if args.exchange == "cabi":
+            return join.probe(k, out_key, out_payload, result[0])
         if args.exchange in ("p2p", "ce"):
             return join.probe_pipelined(k, n_sub, out_key, out_payload, result)
         shuffled = join.shuffle(k, out=recv_buf)
@@ -412,7 +421,7 @@ def main() -> int:
             for b in range(1 if dense else n_sub):
                 m = min(int(rr[b, 0]), cap if dense else capb)
                 rows = out_key[b * capb:b * capb + m]
-                owner = (pkg.murmurhash64(rows) >> (64 - join.log2p)) & (world - 1)
+                owner = (pkg.murmurhash64(rows.contiguous()) >> (64 - join.log2p)) & (world - 1)
                 owned_ok = owned_ok and bool((owner == rank).all().item()) and bool((out_payload[b * capb:b * capb + m] == rows).all().item())
             t = torch.tensor([int(owned_ok)], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -455,7 +464,7 @@ def main() -> int:
         t = torch.tensor([expected_sum - (1 << 64) if expected_sum >= (1 << 63) else expected_sum], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         expected_sum = int(t.item()) & ((1 << 64) - 1)
-    if distributed and join.copier is not None:
+    if distributed and getattr(join, "copier", None) is not None:
         join.copier.check_overflow()
     assert overflow == 0, "output capacity overflow"
     assert n_matches == n_probe * world, (n_matches, n_probe * world)
@@ -468,7 +477,7 @@ def main() -> int:
             "data": "synthetic", "config": workload_config(args), "gpu_launches": int(launches), "clocks": clocks,
             "build_seconds": build_s, "table": {"n_keys": int(info.n_keys), "n_slots": int(info.n_slots), "bytes": int(info.bytes)},
             "checks": {"n_matches": n_matches, "key_sum_ok": True, "owner_property": True if distributed else None}}
-    if distributed:
+    if distributed and hasattr(join, "build_phases"):
         line["build_phases"] = {k: round(v, 3) for k, v in join.build_phases.items()}
 
     if rank == 0 or not distributed:
@@ -477,7 +486,7 @@ def main() -> int:
             kernel_ms = statistics.mean(step_ms)
             achieved = ALGO_BYTES_PER_TUPLE * n_probe / (kernel_ms * 1e-3) / 1e9
             ph = [statistics.mean(p[i] for p in phase_ms) for i in range(3)] if phase_ms else [0, 0, 0]
-            tb = int(info.bytes)
+            tb = int(info.n_slots) * 8  # the LP slot array (the occupancy bitmap beside it is not read by the batch probe)
             kernels = [  # live CUDA-event time of every kernel of the step with its own algorithmic bytes
                 {"kernel": "partition_count_kernel", "ms": ph[0], "algorithmic_bytes": 8 * n_probe},
                 {"kernel": "partition_scatter_kernel", "ms": ph[1], "algorithmic_bytes": 16 * n_probe},
@@ -540,7 +549,8 @@ def main() -> int:
                                     dense=n_sub == 1 or (args.exchange == "ce" and join.ce_probe == "stream"), cap=cap, step=step,
                                     result=result, out_key=out_key, out_payload=out_payload,
                                     gen_keys=lambda n, first: pkg.gen_keys_counter(n, 2, key_space - 1, first=first),
-                                    iters=max(3, args.steps), host_step=lambda hk, hok, hop: join.probe_host(hk, hok, hop, n_sub=n_sub))
+                                    iters=max(3, args.steps),
+                                    host_step=(lambda hk, hok, hop: join.probe_host(hk, hok, hop, n_sub=n_sub)) if hasattr(join, "probe_host") else None)
         line["e2e"] = e2e
         if note:
             line["e2e_note"] = note

@@ -113,6 +113,7 @@ SIGNATURES = {
     "cc_launch_count": (_u64, []),
     "cc_hash_u64": (_int, [_vp, _vp, _sz, _vp]),
     "cc_gen_build_keys": (_int, [_vp, _sz, _sz, _vp]),
+    "cc_gen_build_keys_range": (_int, [_vp, _sz, _sz, _sz, _sz, _vp]),
     "cc_gen_keys_counter": (_int, [_vp, _sz, _u64, _u64, _u64, _vp]),
     "cc_ht_build": (_int, [_pvp, _int, _vp, _sz, _int, _vp]),
     "cc_ht_build_sized": (_int, [_pvp, _int, _vp, _sz, _sz, _int, _vp]),
@@ -174,6 +175,22 @@ SIGNATURES = {
     "cc_ipc_open": (_int, [_vp, _pvp]),
     "cc_ipc_close": (_int, [_vp]),
 }
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class Comm(C.Structure):
+    """cc_comm: the caller's control plane for cc_pjoin_create / cc_pjoin_destroy"""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather", ALLGATHER_FN), ("barrier", BARRIER_FN), ("user", C.c_void_p)]
+
+
+SIGNATURES.update({
+    "cc_pjoin_create": (_int, [_pvp, C.POINTER(Comm), _int, _vp, _sz, _sz, _int, _vp]),
+    "cc_pjoin_probe": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "cc_pjoin_table": (_int, [_vp, _pvp]),
+    "cc_pjoin_destroy": (_int, [_vp]),
+})
 
 _lib = None
 

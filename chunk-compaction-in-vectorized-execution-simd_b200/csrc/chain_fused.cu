@@ -44,6 +44,7 @@ struct ChainLevel {
   const uint64_t *slots;
   const uint2 *dir;
   const int64_t *ckeys;
+  const uint32_t *occ;  // occupancy bitmap of the buckets / slots (cc_ht::d_occ)
   uint64_t mask;
   const int64_t *col;  // LHS join-key column of this level
   uint32_t need;       // rows that must be cached before the next join runs (1..kW)
@@ -345,22 +346,28 @@ struct WarpShared {
   uint32_t active[CC_MAX_JOINS];
 };
 
+constexpr int kWarpsPerCta = 4;  // independent pipeline instances per CTA (a CTA is only a container: 32 CTAs per SM would cap the warps)
+__host__ __device__ constexpr size_t chain_warp_smem(int n_joins, int W) {
+  return (sizeof(WarpShared) + (size_t) n_joins * 3 * (2 * W) * sizeof(uint32_t) + (size_t) (n_joins - 1) * (4 * W) * sizeof(uint32_t) + 15) & ~(size_t) 15;
+}
+
 template <int R>
-__global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 : 3)) chain_warp_kernel(ChainArgs a) {
   static_assert(R >= 1 && R <= 4, "the match ranks of a round are packed into four 16-bit fields");
   constexpr int W = 32 * R;       // rows per chunk of this pipeline instance
   constexpr int SC = 2 * W;       // scan[L]: a probe step may add W lanes to W - 1 waiting ones
-  constexpr int BC = 5 * W;       // chunk[L]: rounds are narrowed so that their matches always fit (see `limit`)
+  constexpr int BC = 4 * W;       // chunk[L]: a round emits only the matches that fit, the other lanes wait (see `room`)
   constexpr int KSC = 8;          // chain entries inspected per lane and round (two sectors: a 5-entry chain ends in one round)
   constexpr int KSL = 4;          // LP slots inspected per lane and round
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  unsigned char *smem_raw = smem_all + (threadIdx.x >> 5) * chain_warp_smem(a.n_joins, W);  // this warp's private slice
   WarpShared &S = *reinterpret_cast<WarpShared *>(smem_raw);
   uint32_t *sc_row = reinterpret_cast<uint32_t *>(smem_raw + sizeof(WarpShared));  // [J][SC]
   uint32_t *sc_pos = sc_row + a.n_joins * SC;
   uint32_t *sc_end = sc_pos + a.n_joins * SC;
   uint32_t *bufs = sc_end + a.n_joins * SC;  // chunk[L] for L = 1 .. J-1 at bufs + (L-1)*BC
   const int J = a.n_joins;
-  const unsigned lane = threadIdx.x, lt = lanemask_lt();
+  const unsigned lane = threadIdx.x & 31u, lt = lanemask_lt();
   const auto need_of = [&](int l) -> uint32_t {  // threshold of the compactor behind join l, on this instance's chunk width
     const uint32_t t = (a.lv[l].need * (uint32_t) W + (uint32_t) kW - 1u) / (uint32_t) kW;
     return t < 1u ? 1u : (t > (uint32_t) W ? (uint32_t) W : t);
@@ -403,14 +410,10 @@ __global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
       const ChainLevel &lv = a.lv[L];
       const bool chain = lv.kind == CC_HT_CHAIN;
       const uint32_t ks = chain ? (uint32_t) KSC : (uint32_t) KSL;
-      uint32_t limit = (uint32_t) W;
-      if (L + 1 < J) {  // every lane may emit ks matches: take only as many lanes as the next chunk can absorb
-        const uint32_t room = ((uint32_t) BC - S.bufcnt[L + 1]) / ks;
-        limit = room < limit ? room : limit;
-      }
-      const uint32_t lanes = n_act < limit ? n_act : limit;
+      (void) ks;
+      const uint32_t lanes = n_act < (uint32_t) W ? n_act : (uint32_t) W;
       const uint32_t first = n_act - lanes;  // the LAST `lanes` entries of the scan are processed
-      uint32_t row[R], p[R], e[R], m[R];
+      uint32_t row[R], p[R], p0[R], e[R], m[R];
       bool still[R];
       uint64_t key[R];
 #pragma unroll
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
           p[i] = sc_pos[L * SC + first + idx];
           e[i] = sc_end[L * SC + first + idx];
         }
+        p0[i] = p[i];
       }
 #pragma unroll
       for (int i = 0; i < R; ++i) key[i] = row[i] != kNoRow ? (uint64_t) __ldg(lv.col + row[i]) : 0ull;
@@ -463,20 +467,6 @@ __global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
         for (int i = 0; i < R; ++i)
           if (m[i]) still[i] = false;
       }
-      __syncwarp();  // every lane has read its scan entries: the tail may be rewritten
-      // AdvancePointers: surviving lanes stay in the scan, compacted in place at the tail
-      uint32_t sbase = first;
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const unsigned bal = __ballot_sync(0xffffffffu, still[i]);
-        if (still[i]) {
-          const uint32_t o = sbase + __popc(bal & lt);
-          sc_row[L * SC + o] = row[i];
-          sc_pos[L * SC + o] = p[i];
-          sc_end[L * SC + o] = e[i];
-        }
-        sbase += __popc(bal);
-      }
       // rank the matches: ONE warp scan over the kR per-lane counts packed into 16-bit fields (a field sums to <= 32 * 8)
       uint64_t packed = 0;
 #pragma unroll
@@ -496,12 +486,59 @@ __global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
         total += (uint32_t) ((tot >> (16 * i)) & 0xFFFFu);
       }
       if (L + 1 < J) {
+        // The next level's chunk takes what fits.  Ranks grow with the entry index, so the entries that fit are a prefix; an
+        // entry beyond it is put back as it was (position restored, still waiting) and emits nothing in this round.  At least
+        // one entry always fits: the chunk holds fewer than W rows here (else the state machine had descended) and an entry
+        // emits at most KSC <= BC - W matches.
+        const uint32_t room = (uint32_t) BC - S.bufcnt[L + 1];
+        if (total > room) {
+          uint32_t fit_end = 0;
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            if (off[i] + m[i] > room) {
+              if (row[i] != kNoRow) {
+                p[i] = p0[i];
+                still[i] = true;
+              }
+              m[i] = 0;
+            } else {
+              fit_end = off[i] + m[i] > fit_end ? off[i] + m[i] : fit_end;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t t = __shfl_xor_sync(0xffffffffu, fit_end, o);
+            fit_end = t > fit_end ? t : fit_end;
+          }
+          total = fit_end;
+        }
+      }
+      __syncwarp();  // every lane has read its scan entries: the tail may be rewritten
+      // AdvancePointers: surviving lanes stay in the scan, compacted in place at the tail
+      uint32_t sbase = first;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const unsigned bal = __ballot_sync(0xffffffffu, still[i]);
+        if (still[i]) {
+          const uint32_t o = sbase + __popc(bal & lt);
+          sc_row[L * SC + o] = row[i];
+          sc_pos[L * SC + o] = p[i];
+          sc_end[L * SC + o] = e[i];
+        }
+        sbase += __popc(bal);
+      }
+      if (L + 1 < J) {
         // Compact: append the matching rows densely to the next level's cached chunk
         const uint32_t cnt0 = S.bufcnt[L + 1];
         uint32_t *dst = bufs + L * BC + cnt0;
 #pragma unroll
-        for (int i = 0; i < R; ++i)
-          for (uint32_t q = 0; q < m[i]; ++q) dst[off[i] + q] = row[i];
+        for (int i = 0; i < R; ++i) {
+          if (m[i]) {
+            // the row will be probed at the next level soon: pull its key there into L2 now, off the critical path
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.lv[L + 1].col + row[i]));
+            for (uint32_t q = 0; q < m[i]; ++q) dst[off[i] + q] = row[i];
+          }
+        }
         __syncwarp();
         if (lane == 0) S.bufcnt[L + 1] = cnt0 + total;
       } else if (total) {
@@ -575,25 +612,27 @@ __global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
       for (int i = 0; i < R; ++i) h[i] = row[i] != kNoRow ? (murmurhash64((uint64_t) __ldg(lv.col + row[i])) & lv.mask) : 0ull;
       uint32_t pos[R], end[R];
       bool act[R];
+      // empty bucket / empty first slot (chaining_ht.cpp:52-55, linear_probing_ht.cpp:53-57): answered by the occupancy bitmap,
+      // which is small enough to stay in L2 -- only the lanes that pass touch the bucket directory
+      uint32_t ow[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) ow[i] = row[i] != kNoRow ? __ldg(lv.occ + (h[i] >> 5)) : 0u;
+#pragma unroll
+      for (int i = 0; i < R; ++i) act[i] = ((ow[i] >> ((uint32_t) h[i] & 31u)) & 1u) != 0u;
       if (lv.kind == CC_HT_CHAIN) {
         uint2 d[R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) d[i] = row[i] != kNoRow ? __ldg(lv.dir + h[i]) : make_uint2(0u, 0u);
+        for (int i = 0; i < R; ++i) d[i] = act[i] ? __ldg(lv.dir + h[i]) : make_uint2(0u, 0u);
 #pragma unroll
         for (int i = 0; i < R; ++i) {
           pos[i] = d[i].x;
           end[i] = d[i].x + d[i].y;
-          act[i] = d[i].y != 0;
         }
       } else {
-        uint64_t v[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) v[i] = row[i] != kNoRow ? ld_nc_u64(lv.slots + h[i]) : kEmptyU;
 #pragma unroll
         for (int i = 0; i < R; ++i) {
           pos[i] = (uint32_t) h[i];
           end[i] = 0;
-          act[i] = v[i] != kEmptyU;
         }
       }
       uint32_t n_valid = 0;
@@ -662,14 +701,14 @@ __global__ void __launch_bounds__(32) chain_warp_kernel(ChainArgs a) {
 template <int R>
 static int launch_chain_warp(const ChainArgs &a, size_t n_joins, cudaStream_t st) {
   constexpr int W = 32 * R;
-  const size_t smem = sizeof(WarpShared) + n_joins * 3 * (size_t) (2 * W) * sizeof(uint32_t) + (n_joins - 1) * (size_t) (5 * W) * sizeof(uint32_t);
+  const size_t smem = chain_warp_smem((int) n_joins, W) * kWarpsPerCta;
   CC_CUDA(cudaFuncSetAttribute(chain_warp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int per_sm = 0;
-  CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_warp_kernel<R>, 32, smem));
+  CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_warp_kernel<R>, 32 * kWarpsPerCta, smem));
   if (per_sm < 1) per_sm = 1;
   const size_t ntiles = (a.n_rows + W - 1) / W;
-  const size_t grid = std::min<size_t>(ntiles, (size_t) sm_count() * per_sm);
-  chain_warp_kernel<R><<<(unsigned) grid, 32, smem, st>>>(a);
+  const size_t grid = std::min<size_t>((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, (size_t) sm_count() * per_sm);
+  chain_warp_kernel<R><<<(unsigned) grid, 32 * kWarpsPerCta, smem, st>>>(a);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -712,6 +751,7 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
     lv.slots = t->d_slots;
     lv.dir = t->d_dir;
     lv.ckeys = t->d_ckeys;
+    lv.occ = t->d_occ;
     lv.mask = t->mask;
     lv.col = h_lhs_cols[l];
     lv.kind = t->kind;
@@ -727,14 +767,14 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
   CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_chain_result), st));
   chain_init_kernel<<<1, 32, 0, st>>>(d_result);
   CC_CHECK_LAUNCH();
-  // measurement switch: CCB_CHAIN_IMPL = cta (the round-1 CTA-wide kernel), w1 / w2 / w4 (warp pipelines, rows per lane); default w4
+  // measurement switch: CCB_CHAIN_IMPL = cta (the round-1 CTA-wide kernel), w1 / w2 / w4 (warp pipelines, rows per lane); default w2 (measured: profiles/r2_chain_variants.txt)
   static const int impl = [] {
     const char *e = getenv("CCB_CHAIN_IMPL");
-    if (!e) return 4;
+    if (!e) return 2;
     if (!strcmp(e, "cta")) return 0;
-    if (!strcmp(e, "w2")) return 2;
     if (!strcmp(e, "w1")) return 1;
-    return 4;
+    if (!strcmp(e, "w4")) return 4;
+    return 2;
   }();
   if (n_rows && impl != 0) {
     CC_TRY(impl == 1 ? launch_chain_warp<1>(a, n_joins, st) : impl == 2 ? launch_chain_warp<2>(a, n_joins, st) : launch_chain_warp<4>(a, n_joins, st));

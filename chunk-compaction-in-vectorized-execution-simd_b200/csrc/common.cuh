@@ -115,6 +115,10 @@ struct cc_ht {
   uint2 *d_dir;
   int64_t *d_ckeys;
   uint32_t *d_rowid;  // build-side row id of each chain entry (payload hook)
+  // occupancy bitmap: bit i set <=> bucket i is non-empty (chain) / slot i holds a key (LP).  It answers the reference's
+  // "drop lanes with an empty bucket / first slot" (chaining_ht.cpp:52-55, linear_probing_ht.cpp:53-57) from 1 bit per
+  // entry -- 64x smaller than the directory, so it stays L2-resident where the directories of a join chain do not.
+  uint32_t *d_occ;
   int has_duplicates;
   size_t max_chain;
   size_t bytes;

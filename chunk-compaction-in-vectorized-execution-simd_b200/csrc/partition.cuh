@@ -65,4 +65,10 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
 int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,
                       cudaStream_t st);
 
+// probe a SEGMENTED key column (probe_batch.cu); accumulate: keep the running match count / output position of earlier calls
+int probe_segmented_device(const cc_ht *ht, const int64_t *d_keys, SegIn seg, int64_t *d_out_key, int64_t *d_out_payload, size_t cap,
+                           cc_probe_result *d_result, cudaStream_t st, bool accumulate);
+// closes a result that was accumulated over several probes: overflow bit 0 = out_capacity too small, bit 1 = *d_region_flag set
+int probe_close_device(cc_probe_result *d_result, size_t cap, const int *d_region_flag, cudaStream_t st);
+
 }  // namespace ccb

@@ -1231,9 +1231,11 @@ struct PayIO {
   unsigned long long *col_sum = nullptr;
 };
 
+// accumulate: *d_result is NOT cleared -- the rows of this call continue behind those of earlier calls (same output columns, one
+// running match count), the way the pieces of an incremental probe do
 int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
                        uint64_t *d_out_rowid, size_t cap, cc_probe_result *d_result, cudaStream_t st, SegIn seg = SegIn(),
-                       PayIO pay = PayIO()) {
+                       PayIO pay = PayIO(), bool accumulate = false) {
   ProbeArgs a;
   a.n_pay = pay.n;
   a.col_sum = pay.col_sum;
@@ -1261,7 +1263,7 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
   a.seg_parts = 0;
   a.gate = nullptr;
   a.gate_want = 0;
-  CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
+  if (!accumulate) CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
   if (n) {
     const bool part = want_partitioned(ht, n, d_out_rowid, pay.n);
     size_t table_bytes = probed_table_bytes(ht, pay.n);
@@ -1359,6 +1361,18 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
     probe_finish_kernel<<<1, 32, 0, st>>>(d_result, a.cap);
     CC_CHECK_LAUNCH();
   }
+  return CC_OK;
+}
+
+// entry points for pjoin.cu (partition.cuh)
+int probe_segmented_device(const cc_ht *ht, const int64_t *d_keys, SegIn seg, int64_t *d_out_key, int64_t *d_out_payload, size_t cap,
+                           cc_probe_result *d_result, cudaStream_t st, bool accumulate) {
+  return probe_batch_device(ht, d_keys, (size_t) seg.segments * seg.cap, d_out_key, d_out_payload, nullptr, cap, d_result, st, seg, PayIO(), accumulate);
+}
+
+int probe_close_device(cc_probe_result *d_result, size_t cap, const int *d_region_flag, cudaStream_t st) {
+  probe_finish_kernel<<<1, 32, 0, st>>>(d_result, cap, d_region_flag);
+  CC_CHECK_LAUNCH();
   return CC_OK;
 }
 

@@ -66,9 +66,9 @@ __global__ void hash_kernel(const uint64_t *__restrict__ in, uint64_t *__restric
 }
 
 // chaining_ht.cpp:15-26: key of build row r is (r / cf) * step with step = n / num_unique.
-__global__ void gen_build_keys_kernel(int64_t *__restrict__ keys, size_t n, size_t cf, size_t step) {
+__global__ void gen_build_keys_kernel(int64_t *__restrict__ keys, size_t n, size_t cf, size_t step, size_t first = 0) {
   size_t stride = (size_t) gridDim.x * blockDim.x;
-  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) keys[i] = (int64_t) ((i / cf) * step);
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) keys[i] = (int64_t) (((first + i) / cf) * step);
 }
 
 __global__ void gen_keys_counter_kernel(int64_t *__restrict__ keys, size_t n, uint64_t seed, uint64_t first, uint64_t mask) {
@@ -241,6 +241,18 @@ int cc_gen_build_keys(int64_t *d_keys, size_t n, size_t cf, cc_stream_t s) {
   size_t num_unique = n / cf + (n % cf != 0);
   size_t step = n / num_unique;
   gen_build_keys_kernel<<<grid_for(n, 256), 256, 0, as_stream(s)>>>(d_keys, n, cf, step);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_gen_build_keys_range(int64_t *d_keys, size_t first, size_t count, size_t n_total, size_t cf, cc_stream_t s) {
+  CC_TRY(require_device());
+  if (count == 0) return CC_OK;
+  CC_REQUIRE(d_keys && cf > 0, "NULL buffer or chunk_factor == 0");
+  CC_REQUIRE(first + count <= n_total, "rows [%zu, %zu) exceed the %zu build rows", first, first + count, n_total);
+  size_t num_unique = n_total / cf + (n_total % cf != 0);
+  size_t step = n_total / num_unique;
+  gen_build_keys_kernel<<<grid_for(count, 256), 256, 0, as_stream(s)>>>(d_keys, count, cf, step, first);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

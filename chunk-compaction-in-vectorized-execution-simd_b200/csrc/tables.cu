@@ -431,8 +431,36 @@ static int build_chain(cc_ht *ht, const int64_t *d_keys, size_t n, cudaStream_t 
   return CC_OK;
 }
 
+// one bit per bucket / slot (see cc_ht::d_occ)
+__global__ void occupancy_kernel(const uint64_t *__restrict__ slots, const uint2 *__restrict__ dir, size_t n, uint32_t *__restrict__ occ) {
+  const size_t words = (n + 31) / 32;
+  const size_t warps = ((size_t) gridDim.x * blockDim.x) >> 5;
+  for (size_t wi = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < words; wi += warps) {
+    const size_t i = wi * 32 + (threadIdx.x & 31);
+    bool bit = false;
+    if (i < n) bit = slots ? slots[i] != kEmptyU : dir[i].y != 0u;
+    const unsigned w = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0) occ[wi] = w;
+  }
+}
+
+static int build_occupancy(cc_ht *ht, cudaStream_t st) {
+  const size_t words = (ht->n_slots + 31) / 32;
+  if (ht->d_occ) cudaFree(ht->d_occ);
+  ht->d_occ = nullptr;
+  CC_CUDA(cudaMalloc(&ht->d_occ, words * sizeof(uint32_t)));
+  ht->bytes += words * sizeof(uint32_t);
+  size_t blocks = (words * 32 + 255) / 256;
+  const size_t cap = (size_t) sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  occupancy_kernel<<<(unsigned) blocks, 256, 0, st>>>(ht->kind == CC_HT_LP ? ht->d_slots : nullptr, ht->d_dir, ht->n_slots, ht->d_occ);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
 static void free_table(cc_ht *ht) {
   if (!ht) return;
+  if (ht->d_occ) cudaFree(ht->d_occ);
   if (ht->d_slots) cudaFree(ht->d_slots);
   if (ht->d_dir) cudaFree(ht->d_dir);
   if (ht->d_ckeys) cudaFree(ht->d_ckeys);
@@ -467,6 +495,7 @@ int cc_ht_build_sized(cc_ht **out, int kind, const int64_t *d_keys, size_t n, si
   ht->n_keys = n;
   cudaGetDevice(&ht->device);
   int rc = kind == CC_HT_LP ? build_lp(ht, d_keys, n, flags, as_stream(s), n_slots) : build_chain(ht, d_keys, n, as_stream(s), n_slots);
+  if (rc == CC_OK) rc = build_occupancy(ht, as_stream(s));
   if (rc != CC_OK) {
     free_table(ht);
     return rc;
@@ -630,6 +659,12 @@ int cc_ht_import_lp(cc_ht **out, const int64_t *h_slots, size_t n_slots, size_t 
     return CC_ERR_CUDA;
   }
   ht->bytes = n_slots * sizeof(uint64_t);
+  int rc = build_occupancy(ht, as_stream(s));
+  if (rc == CC_OK && cudaStreamSynchronize(as_stream(s)) != cudaSuccess) rc = CC_ERR_CUDA;
+  if (rc != CC_OK) {
+    free_table(ht);
+    return rc;
+  }
   *out = ht;
   return CC_OK;
 }

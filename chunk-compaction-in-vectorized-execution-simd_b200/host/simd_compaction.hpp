@@ -386,4 +386,144 @@ class CompactTuner {
   cc_tuner *t_ = nullptr;
 };
 
+
+// ---- partitioned multi-GPU join (new functionality; cc_pjoin_* of the C ABI) -------------------------------
+// LocalComm: the control plane for ONE NODE without any library -- the ranks are processes forked from one parent AFTER the
+// communicator was created (and BEFORE any of them touches CUDA), talking through an anonymous shared mapping: a
+// sense-reversing barrier and a staging area for all-gathers.  Hand `Comm()` to cc_pjoin_create / PartitionedJoin.
+}  // namespace simd_compaction
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstring>
+namespace simd_compaction {
+
+class LocalComm {
+ public:
+  static constexpr size_t kSlotBytes = 256;
+  explicit LocalComm(int world) : world_(world) {
+    const size_t bytes = sizeof(Shared) + (size_t) world * kSlotBytes;
+    void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) throw std::runtime_error("LocalComm: mmap failed");
+    sh_ = new (m) Shared();
+    slots_ = reinterpret_cast<unsigned char *>(m) + sizeof(Shared);
+    bytes_ = bytes;
+  }
+  ~LocalComm() { munmap(sh_, bytes_); }
+  // forks world - 1 children; returns this process's rank (the parent is rank 0)
+  int Fork() {
+    for (int r = 1; r < world_; ++r) {
+      pid_t pid = fork();
+      if (pid < 0) throw std::runtime_error("LocalComm: fork failed");
+      if (pid == 0) {
+        rank_ = r;
+        children_.clear();
+        return r;
+      }
+      children_.push_back(pid);
+    }
+    rank_ = 0;
+    return 0;
+  }
+  // rank 0: waits for the children; returns true if all of them exited with status 0
+  bool Join() {
+    bool ok = true;
+    for (pid_t pid : children_) {
+      int st = 0;
+      if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) ok = false;
+    }
+    children_.clear();
+    return ok;
+  }
+  void Barrier() {
+    const unsigned sense = local_sense_ ^= 1u;
+    if (sh_->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == (unsigned) world_) {
+      sh_->arrived.store(0, std::memory_order_relaxed);
+      sh_->sense.store(sense, std::memory_order_release);
+    } else {
+      // a rank that failed never arrives: give up instead of waiting for it forever
+      for (unsigned long spins = 0; sh_->sense.load(std::memory_order_acquire) != sense; ++spins) {
+        if (sh_->failed.load(std::memory_order_acquire)) throw std::runtime_error("LocalComm: a peer rank failed");
+        if (spins > 2400000ul) throw std::runtime_error("LocalComm: barrier timed out (120 s)");
+        usleep(50);
+      }
+    }
+  }
+  void Fail() { sh_->failed.store(1, std::memory_order_release); }  // call before leaving on an error: releases the waiting peers
+  void AllGather(const void *send, void *recv, size_t bytes) {
+    if (bytes > kSlotBytes) throw std::runtime_error("LocalComm: all-gather record too large");
+    std::memcpy(slots_ + (size_t) rank_ * kSlotBytes, send, bytes);
+    Barrier();
+    for (int r = 0; r < world_; ++r) std::memcpy(static_cast<unsigned char *>(recv) + (size_t) r * bytes, slots_ + (size_t) r * kSlotBytes, bytes);
+    Barrier();
+  }
+  cc_comm Comm() {
+    cc_comm c;
+    c.rank = rank_;
+    c.world = world_;
+    c.user = this;
+    c.allgather = [](void *u, const void *s, void *r, size_t b) -> int {
+      try {
+        static_cast<LocalComm *>(u)->AllGather(s, r, b);
+        return 0;
+      } catch (...) {
+        return 1;
+      }
+    };
+    c.barrier = [](void *u) -> int {
+      try {
+        static_cast<LocalComm *>(u)->Barrier();
+        return 0;
+      } catch (...) {
+        return 1;
+      }
+    };
+    return c;
+  }
+  int Rank() const { return rank_; }
+  int World() const { return world_; }
+
+ private:
+  struct Shared {
+    std::atomic<unsigned> arrived{0};
+    std::atomic<unsigned> sense{0};
+    std::atomic<unsigned> failed{0};
+  };
+  Shared *sh_ = nullptr;
+  unsigned char *slots_ = nullptr;
+  size_t bytes_ = 0;
+  int world_ = 1, rank_ = 0;
+  unsigned local_sense_ = 0;
+  vector<pid_t> children_;
+};
+
+// The partitioned join as a class: build once (collective), probe many times (collective, one call per rank and step).
+class PartitionedJoin {
+ public:
+  PartitionedJoin(const cc_comm &comm, int kind, const Attribute *d_build_keys, size_t n_build_local, size_t max_probe_rows, int n_sub = 4) {
+    Check(cc_pjoin_create(&h_, &comm, kind, d_build_keys, n_build_local, max_probe_rows, n_sub, nullptr));
+  }
+  PartitionedJoin(const PartitionedJoin &) = delete;
+  PartitionedJoin &operator=(const PartitionedJoin &) = delete;
+  ~PartitionedJoin() {
+    if (h_) cc_pjoin_destroy(h_);
+  }
+  // enqueues partition + exchange + probe of this rank's keys; nothing is synchronised
+  void Probe(const Attribute *d_keys, size_t n, Attribute *d_out_key, Attribute *d_out_payload, size_t out_capacity, cc_probe_result *d_result) {
+    Check(cc_pjoin_probe(h_, d_keys, n, d_out_key, d_out_payload, out_capacity, d_result, nullptr));
+  }
+  cc_ht_info TableInfo() const {
+    const cc_ht *t = nullptr;
+    Check(cc_pjoin_table(h_, &t));
+    cc_ht_info i;
+    Check(cc_ht_get_info(t, &i));
+    return i;
+  }
+
+ private:
+  cc_pjoin *h_ = nullptr;
+};
+
 }  // namespace simd_compaction

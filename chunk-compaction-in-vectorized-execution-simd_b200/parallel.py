@@ -535,6 +535,85 @@ class PartitionedJoin:
         return self.table.probe_batch(keys, **kw)
 
 
+def make_comm(pkg, group=None):
+    """cc_comm (include/cc_api.h) on top of torch.distributed: the control plane of the C-ABI partitioned join.  Returns the
+    ctypes struct; it keeps its callbacks alive.  Works with NCCL (staging through device tensors) and gloo."""
+    import ctypes as C
+
+    L = pkg._lib
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+
+    def allgather(user, send, recv, nbytes):
+        try:
+            mine = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8).to(dev)
+            out = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, mine, group=group)
+            C.memmove(recv, out.cpu().numpy().tobytes(), world * nbytes)
+            return 0
+        except Exception:  # noqa: BLE001 -- reported to the C side as a failed callback
+            return 1
+
+    def barrier(user):
+        try:
+            dist.barrier(group=group)
+            return 0
+        except Exception:  # noqa: BLE001
+            return 1
+
+    comm = L.Comm()
+    comm.rank, comm.world = rank, world
+    comm._ag, comm._ba = L.ALLGATHER_FN(allgather), L.BARRIER_FN(barrier)  # keep the trampolines alive
+    comm.allgather, comm.barrier, comm.user = comm._ag, comm._ba, None
+    return comm
+
+
+class CPartitionedJoin:
+    """The partitioned join entirely behind the C ABI (cc_pjoin_*, csrc/pjoin.cu): partition kernels, copy-engine block copies
+    into IPC-mapped peer memory and device-side ready / consumed flags -- no collective on the data path; torch.distributed is
+    only the control plane (IPC handles and sizes at create, a barrier at destroy).  A C or C++ host does the same with its own
+    cc_comm (host/simd_compaction.hpp: LocalComm, host/pjoin_main.cpp)."""
+
+    def __init__(self, pkg, kind: int, local_build_keys: torch.Tensor, max_probe_rows: int, n_sub: int = 4, group=None):
+        import ctypes as C
+
+        self.pkg, self.group = pkg, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.log2p = log2_exact(self.world)
+        self.n_sub = n_sub
+        self._comm = make_comm(pkg, group)
+        h = C.c_void_p()
+        n = local_build_keys.numel()
+        pkg._lib.check(pkg.lib().cc_pjoin_create(C.byref(h), C.byref(self._comm), kind, local_build_keys.data_ptr() if n else None, n,
+                                                  int(max_probe_rows), int(n_sub), torch.cuda.current_stream().cuda_stream))
+        self._h = h
+
+    def table_info(self):
+        import ctypes as C
+
+        t = C.c_void_p()
+        self.pkg._lib.check(self.pkg.lib().cc_pjoin_table(self._h, C.byref(t)))
+        i = self.pkg._lib.HtInfo()
+        self.pkg._lib.check(self.pkg.lib().cc_ht_get_info(t, C.byref(i)))
+        return i
+
+    def probe(self, local_probe_keys: torch.Tensor, out_key: Optional[torch.Tensor], out_payload: Optional[torch.Tensor], result: torch.Tensor) -> None:
+        """Enqueues partition + exchange + probe of this rank's keys on the current stream (collective; nothing is synchronised).
+        result: int64[4] device tensor (cc_probe_result); the rows this rank owns land densely in out_key / out_payload."""
+        n = local_probe_keys.numel()
+        cap = out_key.numel() if out_key is not None else (out_payload.numel() if out_payload is not None else 0)
+        self.pkg._lib.check(self.pkg.lib().cc_pjoin_probe(self._h, local_probe_keys.data_ptr() if n else None, n,
+                                                           out_key.data_ptr() if out_key is not None else None,
+                                                           out_payload.data_ptr() if out_payload is not None else None, cap,
+                                                           result.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            h, self._h = self._h, None
+            self.pkg._lib.check(self.pkg.lib().cc_pjoin_destroy(h))
+
+
 def reduce_result(n_matches: int, key_sum: int, payload_sum: int, device, group=None) -> Tuple[int, int, int]:
     """Sum of the per-rank counts / wrapping checksums (all-reduce of three int64)."""
     def wrap(v):

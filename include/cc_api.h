@@ -105,6 +105,8 @@ int cc_hash_u64(const uint64_t *d_in, uint64_t *d_out, size_t n, cc_stream_t str
 /* --------------------------------------------------------------- generators */
 /* build keys: chaining_ht.cpp:15-26 == linear_probing_ht.cpp:14-25           */
 int cc_gen_build_keys(int64_t *d_keys, size_t n, size_t chunk_factor, cc_stream_t stream);
+/* rows [first, first + count) of the same column for a build side of n_total rows (one rank's share of a partitioned join) */
+int cc_gen_build_keys_range(int64_t *d_keys, size_t first, size_t count, size_t n_total, size_t chunk_factor, cc_stream_t stream);
 /* SURVEY 8d C4/C5 probe keys: d_keys[i] = murmurhash64(seed + first + i) & mask */
 int cc_gen_keys_counter(int64_t *d_keys, size_t n, uint64_t seed, uint64_t first, uint64_t mask, cc_stream_t stream);
 
@@ -403,6 +405,39 @@ typedef struct {
 int cc_ipc_export(void *d_ptr, cc_ipc_handle *out);
 int cc_ipc_open(const cc_ipc_handle *handle, void **d_ptr);
 int cc_ipc_close(void *d_ptr);
+
+/* ------------------------------------------- partitioned multi-GPU join (C5) */
+/* The hash-partitioned join of SURVEY 8e behind the C ABI: one process per GPU, no collective library on the data path.
+ * Both sides are partitioned by owner = murmurhash64(key) >> (64 - log2 world); the sub-batches of a probe call travel as
+ * copy-engine block copies into CUDA-IPC-mapped peer memory (NVLink 5 / NVSwitch) and are announced / released with
+ * device-side flags, so that a call only ENQUEUES work and returns (csrc/pjoin.cu).  Every rank then probes what it owns
+ * with the single-GPU kernels -- per rank the semantics of LPHashTable / HashTable::Probe + Next
+ * (linear_probing_ht.cpp:39-115, chaining_ht.cpp:38-136); the union of the ranks' result rows is the reference's result.
+ *
+ * cc_comm is the caller's CONTROL plane, used collectively and only inside cc_pjoin_create / cc_pjoin_destroy:
+ *   allgather(user, send, recv, bytes): every rank contributes `bytes` bytes, recv gets world * bytes in rank order;
+ *   barrier(user).   Both return 0 on success.  (MPI_Allgather / MPI_Barrier, torch.distributed, or the fork +
+ *   shared-memory communicator of host/simd_compaction.hpp.)                                                          */
+typedef struct cc_pjoin cc_pjoin;
+typedef struct {
+  int rank, world; /* world: a power of two, at most 16 (one NVLink domain) */
+  int (*allgather)(void *user, const void *send, void *recv, size_t bytes);
+  int (*barrier)(void *user);
+  void *user;
+} cc_comm;
+/* Collective.  d_build_keys[n_build_local]: this rank's share of the build side (any split); max_probe_rows: the most probe
+ * keys this rank will pass to one cc_pjoin_probe call; n_sub: sub-batches per call (the exchange of sub-batch b + 1 runs
+ * underneath the probe of sub-batch b).  Every rank's table is sized from the GLOBAL key count (cc_ht_build_sized).       */
+int cc_pjoin_create(cc_pjoin **join, const cc_comm *comm, int kind, const int64_t *d_build_keys, size_t n_build_local,
+                    size_t max_probe_rows, int n_sub, cc_stream_t stream);
+/* Collective (every rank calls it once per step, with its own share of the probe side; n may differ per rank).  Writes
+ * the result rows THIS rank owns densely to d_out_key / d_out_payload (either may be NULL) and one cc_probe_result;
+ * overflow bit 0: out_capacity too small, bit 1: an exchange or slice region overran (heavily skewed keys), bit 2: a
+ * peer never delivered (bounded wait timed out -- the join is unusable afterwards).  Nothing is synchronised.           */
+int cc_pjoin_probe(cc_pjoin *join, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
+                   size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
+int cc_pjoin_table(const cc_pjoin *join, const cc_ht **ht); /* this rank's table (cc_ht_get_info / export) */
+int cc_pjoin_destroy(cc_pjoin *join);                       /* collective */
 
 #ifdef __cplusplus
 }

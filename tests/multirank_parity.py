@@ -105,8 +105,9 @@ def main() -> int:
 
     cfs = (1, 4) if args.quick else (1, 4, 8)
     hits = (2,) if args.quick else (1, 2)
+    # "cabi": the whole partitioned join behind the C ABI (cc_pjoin_*: device-side flags instead of collectives on the data path)
     modes = [("partition", "ce", "stream", 4), ("partition", "ce", "batch", 3), ("partition", "p2p", None, 2), ("partition", "nccl", None, 1),
-             ("broadcast", "nccl", None, 1)]
+             ("partition", "cabi", None, 5), ("broadcast", "nccl", None, 1)]
     for kind, kname in ((pkg.CC_HT_LP, "lp"), (pkg.CC_HT_CHAIN, "chain")):
         OT = O.OracleLP if kind == pkg.CC_HT_LP else O.OracleChain
         for cf in cfs:
@@ -115,12 +116,22 @@ def main() -> int:
             my_build = torch.from_numpy(build_all[rank * nb_local:(rank + 1) * nb_local].copy()).to(dev)
             for plan, exchange, ce_probe, n_sub in modes:
                 cap_rows = -(-np_local // n_sub) if exchange == "ce" else np_local * 4 + nb_local * 4 + (1 << 16)
-                join = par.PartitionedJoin(pkg, kind, my_build, plan=plan, exchange=exchange, capacity_rows=cap_rows,
-                                           ce_probe=ce_probe or "auto")
-                # build side: every key in this rank's table hashes here (partition plan) / the table holds everything (broadcast)
-                exp = join.table.export()
-                tkeys = exp[exp != -1] if kind == pkg.CC_HT_LP else exp[2]
-                if plan == "partition":
+                if exchange == "cabi":
+                    cjoin = par.CPartitionedJoin(pkg, kind, my_build, np_local, n_sub=n_sub)
+                    info = cjoin.table_info()
+                    tot = torch.tensor([int(info.n_keys)], dtype=torch.int64, device=dev)
+                    dist.all_reduce(tot)
+                    own_b = int(tot.item()) == n_build  # (the owner property of the table keys follows from that of the probe rows below)
+                    join = None
+                else:
+                    join = par.PartitionedJoin(pkg, kind, my_build, plan=plan, exchange=exchange, capacity_rows=cap_rows,
+                                               ce_probe=ce_probe or "auto")
+                    # build side: every key in this rank's table hashes here (partition plan) / the table holds everything (broadcast)
+                    exp = join.table.export()
+                    tkeys = exp[exp != -1] if kind == pkg.CC_HT_LP else exp[2]
+                if exchange == "cabi":
+                    pass
+                elif plan == "partition":
                     own_b = bool((owner_of(torch.from_numpy(np.ascontiguousarray(tkeys)).to(dev)) == rank).all().item()) if tkeys.size else True
                     tot = torch.tensor([tkeys.size], dtype=torch.int64, device=dev)
                     dist.all_reduce(tot)
@@ -139,15 +150,17 @@ def main() -> int:
                     try:
                         for rep in range(2):  # twice: the second pass runs on rotated buffers
                             res.zero_()
-                            if plan == "partition" and exchange in ("ce", "p2p"):
+                            if exchange == "cabi":
+                                cjoin.probe(my_probe, ok, op, res[0])
+                            elif plan == "partition" and exchange in ("ce", "p2p"):
                                 join.probe_pipelined(my_probe, n_sub, ok, op, res)
                             else:
                                 join.probe(my_probe, capacity=cap, out_key=ok, out_payload=op, result=res[0], sync=False)
                             torch.cuda.synchronize()
-                        if join.copier is not None:
+                        if join is not None and join.copier is not None:
                             join.copier.check_overflow()
                         rr = res.cpu().numpy().view(np.uint64)
-                        dense = n_sub == 1 or (exchange == "ce" and ce_probe == "stream")
+                        dense = n_sub == 1 or (exchange == "ce" and ce_probe == "stream") or exchange == "cabi"
                         capb = cap // n_sub
                         if dense:
                             m = int(rr[0, 0])
@@ -182,6 +195,10 @@ def main() -> int:
                         say(f"FAIL  {tag}  {type(e).__name__}: {e}")
                         failures.append(tag)
                         raise
+                if join is None:
+                    cjoin.close()
+                    del cjoin
+                    continue
                 if join.copier is not None:
                     join.copier.close()
                 if join.peer is not None:

@@ -169,3 +169,48 @@ def test_bench_distributed_e2e_leg_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, "ok") for r in range(world)], results
+
+
+def _comm_worker(rank: int, world: int, port: int, q):
+    """parallel.make_comm: the cc_comm control plane (include/cc_api.h) over torch.distributed, called the way libccb200 calls it
+    (through the C function pointers), under gloo"""
+    import ctypes as C
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    pkg = importlib.import_module(PKG_NAME)
+    par = importlib.import_module(PKG_NAME + ".parallel")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = par.make_comm(pkg)
+        assert (comm.rank, comm.world) == (rank, world)
+        for nbytes in (8, 64, 24):
+            send = (C.c_ubyte * nbytes)(*[(rank * 37 + i) % 256 for i in range(nbytes)])
+            recv = (C.c_ubyte * (nbytes * world))()
+            assert comm.allgather(None, C.cast(send, C.c_void_p), C.cast(recv, C.c_void_p), nbytes) == 0
+            assert list(recv) == [(r * 37 + i) % 256 for r in range(world) for i in range(nbytes)]
+        assert comm.barrier(None) == 0
+        assert par.table_slots(True, 1 << 30, 134224497, 8) == 1 << 29 and par.table_slots(False, 1 << 30, 134224497, 8) == 1 << 28
+        assert par.table_slots(True, 1000, 900, 2) == 2048  # a skewed partition doubles the LP table instead of overfilling it
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_c_abi_comm_callbacks_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 131
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, "ok") for r in range(world)], results

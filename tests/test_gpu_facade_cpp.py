@@ -65,7 +65,7 @@ def test_cpp_micro_bench_driver(ccb, scale, hit, cf):
     import oracle_lib as O
 
     assert os.path.exists(MICRO), "build it with make -C <pkg>/csrc driver"
-    n_keys = 1 << 20
+    n_keys = 1 << (20 if scale else 17)  # scale 0 = 256-row blocks: one C-ABI call per Probe / Next, 110 s for 2^20 keys
     out = subprocess.check_output([MICRO, "--scale", str(scale), "--hit-frequency", str(hit), "--chunk-factor", str(cf),
                                    "--lhs-tuples", str(n_keys)], timeout=900, stderr=subprocess.DEVNULL)
     r = json.loads(out.decode().strip().splitlines()[-1])
