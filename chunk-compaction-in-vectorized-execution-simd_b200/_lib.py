@@ -89,6 +89,13 @@ class ChainResult(C.Structure):
     ]
 
 
+CC_DENSITY_BINS = 8
+
+
+class ChainTelemetry(C.Structure):
+    _fields_ = [("probe_rows_hist", (C.c_uint64 * CC_DENSITY_BINS) * CC_MAX_JOINS), ("round_lanes_hist", (C.c_uint64 * CC_DENSITY_BINS) * CC_MAX_JOINS)]
+
+
 # every symbol include/cc_api.h declares: (restype, argtypes)
 _vp, _sz, _u64, _int = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int
 _pvp = C.POINTER(C.c_void_p)
@@ -156,6 +163,8 @@ SIGNATURES = {
     "cc_compactor_flush": (_int, [_vp, _pvp, _pvp, C.POINTER(_sz), _vp]),
     "cc_compactor_destroy": (_int, [_vp]),
     "cc_chain_execute": (_int, [_pvp, _sz, _pvp, _sz, _vp, _pvp, _sz, _vp, _vp]),
+    "cc_chain_execute_ex": (_int, [_pvp, _sz, _pvp, _sz, _vp, _pvp, _sz, _vp, _vp, _vp]),
+    "cc_chain_telemetry_csv": (_int, [_vp, _sz, C.c_char_p]),
     "cc_chain_execute_tuned": (_int, [_pvp, _sz, _pvp, _sz, _sz, _vp, _sz, _pvp, _sz, C.POINTER(ChainResult), _vp]),
     "cc_tuner_create": (_int, [_pvp]),
     "cc_tuner_initialize": (_int, [_vp, _sz, _vp, _sz]),

@@ -27,6 +27,7 @@
 // (chaining_ht.cpp:34 drops the payload column), so an intermediate row is fully
 // described by its LHS row id; the result tuple [k_0..k_{J-1}, 0,k_0, 0,k_1, ...]
 //  is rebuilt from the LHS columns at the ResultCollector.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -60,6 +61,7 @@ struct ChainArgs {
   size_t n_rows;
   size_t cap;
   cc_chain_result *res;
+  cc_chain_telemetry *tel;  // optional: chunk-density histograms (the ZebraProfiler analogue, profiler.h:168-260)
 };
 
 struct ChainShared {
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kW, 2) chain_fused_kernel(ChainArgs a) {
     for (int j = 0; j < CC_MAX_JOINS; ++j) S.cs[j] = S.level_in[j] = S.steps[j] = S.lanes[j] = 0, S.active[j] = 0;
     for (int j = 0; j <= CC_MAX_JOINS; ++j) S.bufcnt[j] = 0;
     S.digest = 0;
-    atomicMin((unsigned long long *) &a.res->reserved[1], (unsigned long long) globaltimer_ns());
+    atomicMax((unsigned long long *) &a.res->reserved[1], ~(unsigned long long) globaltimer_ns());  // ~(earliest start): 0-initialised
   }
   __syncthreads();
 
@@ -344,6 +346,7 @@ struct WarpShared {
   unsigned long long level_in[CC_MAX_JOINS], steps[CC_MAX_JOINS], lanes[CC_MAX_JOINS];
   uint32_t bufcnt[CC_MAX_JOINS + 1];
   uint32_t active[CC_MAX_JOINS];
+  uint32_t hist[2][CC_MAX_JOINS][CC_DENSITY_BINS];  // [0]: rows handed to a Probe, [1]: live lanes of a Next round, as a fraction of W
 };
 
 constexpr int kWarpsPerCta = 4;  // independent pipeline instances per CTA (a CTA is only a container: 32 CTAs per SM would cap the warps)
@@ -376,9 +379,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
   if (lane == 0) {
     for (int j = 0; j < CC_MAX_JOINS; ++j) S.level_in[j] = S.steps[j] = S.lanes[j] = 0, S.active[j] = 0;
     for (int j = 0; j <= CC_MAX_JOINS; ++j) S.bufcnt[j] = 0;
-    atomicMin((unsigned long long *) &a.res->reserved[1], (unsigned long long) globaltimer_ns());
+    for (int k = 0; k < 2; ++k)
+      for (int j = 0; j < CC_MAX_JOINS; ++j)
+        for (int q = 0; q < CC_DENSITY_BINS; ++q) S.hist[k][j][q] = 0;
+    atomicMax((unsigned long long *) &a.res->reserved[1], ~(unsigned long long) globaltimer_ns());  // ~(earliest start): 0-initialised
   }
   __syncwarp();
+  // density bin of a chunk of n rows on this instance's width: CC_DENSITY_BINS equal bins over (0, W], full chunks in the last
+  const auto bin_of = [](uint32_t n) -> uint32_t { return n == 0 ? 0u : ((n - 1u) * (uint32_t) CC_DENSITY_BINS) / (uint32_t) W; };
 
   uint64_t cs_acc[CC_MAX_JOINS];  // per-lane partial column sums / digest of the result rows, reduced once at the end
 #pragma unroll
@@ -573,6 +581,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
         S.active[L] = sbase;
         S.steps[L] += 1;
         S.lanes[L] += (unsigned long long) lanes;
+        S.hist[1][L][bin_of(lanes)] += 1;
       }
       __syncwarp();
       continue;
@@ -653,6 +662,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
       if (lane == 0) {
         S.active[L] = base;
         S.level_in[L] += (unsigned long long) n_valid;
+        S.hist[0][L][bin_of(n_valid)] += 1;
       }
       __syncwarp();
       continue;
@@ -696,6 +706,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
     if (digest_acc) atomicAdd((unsigned long long *) &a.res->digest, (unsigned long long) digest_acc);
     atomicMax((unsigned long long *) &a.res->reserved[2], (unsigned long long) globaltimer_ns());
   }
+  if (a.tel) {  // one atomic per non-empty (histogram, level, bin) and warp, lanes share the bins
+    for (int idx = (int) lane; idx < 2 * J * CC_DENSITY_BINS; idx += 32) {
+      const int k = idx / (J * CC_DENSITY_BINS), j = (idx / CC_DENSITY_BINS) % J, q = idx % CC_DENSITY_BINS;
+      const uint32_t v = S.hist[k][j][q];
+      if (v) atomicAdd((unsigned long long *) (k == 0 ? &a.tel->probe_rows_hist[j][q] : &a.tel->round_lanes_hist[j][q]), (unsigned long long) v);
+    }
+  }
 }
 
 template <int R>
@@ -716,13 +733,11 @@ static int launch_chain_warp(const ChainArgs &a, size_t n_joins, cudaStream_t st
 __global__ void chain_finish_kernel(cc_chain_result *res, size_t cap, int materialize) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     res->overflow = (materialize && res->n_tuples > cap) ? 1 : 0;
-    res->device_ns = res->reserved[2] >= res->reserved[1] ? res->reserved[2] - res->reserved[1] : 0;
+    const unsigned long long first = ~res->reserved[1];  // the kernels keep ~(earliest start) there, so a cleared result needs no init pass
+    res->device_ns = (res->reserved[1] != 0 && res->reserved[2] >= first) ? res->reserved[2] - first : 0;
   }
 }
 
-__global__ void chain_init_kernel(cc_chain_result *res) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) res->reserved[1] = ~0ull;
-}
 
 }  // namespace ccb
 
@@ -731,6 +746,12 @@ using namespace ccb;
 extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
                                 const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
                                 cc_chain_result *d_result, cc_stream_t s) {
+  return cc_chain_execute_ex(h_tables, n_joins, h_lhs_cols, n_rows, thresholds, h_out_cols, out_capacity, d_result, nullptr, s);
+}
+
+extern "C" int cc_chain_execute_ex(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
+                                   const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
+                                   cc_chain_result *d_result, cc_chain_telemetry *d_telemetry, cc_stream_t s) {
   CC_TRY(require_device());
   CC_REQUIRE(h_tables && h_lhs_cols && d_result, "NULL argument");
   CC_REQUIRE(n_joins >= 1 && n_joins <= CC_MAX_JOINS, "n_joins must be in [1, %d]", CC_MAX_JOINS);
@@ -741,6 +762,7 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
   a.n_joins = (int) n_joins;
   a.n_rows = n_rows;
   a.res = d_result;
+  a.tel = d_telemetry;  // accumulated into (the caller clears it): histograms of several calls add up
   a.materialize = h_out_cols != nullptr;
   a.cap = a.materialize ? out_capacity : 0;
   for (size_t l = 0; l < n_joins; ++l) {
@@ -765,8 +787,6 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
       a.out[j] = h_out_cols[j];
     }
   CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_chain_result), st));
-  chain_init_kernel<<<1, 32, 0, st>>>(d_result);
-  CC_CHECK_LAUNCH();
   // measurement switch: CCB_CHAIN_IMPL = cta (the round-1 CTA-wide kernel), w1 / w2 / w4 (warp pipelines, rows per lane); default w2 (measured: profiles/r2_chain_variants.txt)
   static const int impl = [] {
     const char *e = getenv("CCB_CHAIN_IMPL");
@@ -795,12 +815,32 @@ extern "C" int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, co
 }
 
 
+// ZebraProfiler-style dump (profiler.h:168-260 writes one CSV row per observed chunk size): one row per histogram, level and bin
+extern "C" int cc_chain_telemetry_csv(const cc_chain_telemetry *h_telemetry, size_t n_joins, const char *path) {
+  CC_REQUIRE(h_telemetry && path, "NULL argument");
+  CC_REQUIRE(n_joins >= 1 && n_joins <= CC_MAX_JOINS, "n_joins must be in [1, %d]", CC_MAX_JOINS);
+  FILE *f = fopen(path, "w");
+  CC_REQUIRE(f, "Unable to open file %s", path);  // negative_feedback.hpp:103-105 / profiler.h throw the same message
+  fprintf(f, "histogram,level,density_from,density_to,chunks\n");
+  for (int k = 0; k < 2; ++k)
+    for (size_t l = 0; l < n_joins; ++l)
+      for (int q = 0; q < CC_DENSITY_BINS; ++q)
+        fprintf(f, "%s,%zu,%.4f,%.4f,%llu\n", k == 0 ? "probe_rows" : "round_lanes", l, (double) q / CC_DENSITY_BINS, (double) (q + 1) / CC_DENSITY_BINS,
+                (unsigned long long) (k == 0 ? h_telemetry->probe_rows_hist[l][q] : h_telemetry->round_lanes_hist[l][q]));
+  fclose(f);
+  return CC_OK;
+}
+
 // Dynamic ("negative feedback") compaction: main.cpp:137-167 under flag_dynamic_compact.
 // The LHS table is processed in batches; before every batch each join's bandit picks a compaction
 // threshold (CompactTuner::SelectArm), the batch runs through the fused kernel, and every bandit is
 // rewarded with the reference's formula  2 / seconds / 1e3  (main.cpp:166) where seconds is the
 // DEVICE time of the batch (globaltimer, cc_chain_result.device_ns) -- a wall-clock reward would be
 // dominated by launch jitter.  Results are accumulated over the batches into *h_result.
+// The batches are PIPELINED kTunedDepth deep: batch i is launched while the results of batches i-1 .. i-kTunedDepth+1 are
+// still on their way back (pinned host records + events), so the GPU never idles for a host round trip between batches; a
+// bandit therefore selects with the feedback of all batches up to i - kTunedDepth (its arithmetic is unchanged: UpdateArm is
+// told which arm a reward belongs to, negative_feedback.hpp:189-195).
 extern "C" int cc_chain_execute_tuned(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
                                       size_t batch_rows, cc_tuner *tuner, size_t first_bandit_id, int64_t *const *h_out_cols,
                                       size_t out_capacity, cc_chain_result *h_result, cc_stream_t s) {
@@ -811,58 +851,88 @@ extern "C" int cc_chain_execute_tuned(const cc_ht *const *h_tables, size_t n_joi
   CC_REQUIRE(cc_tuner_bandit_size(tuner) >= first_bandit_id + n_joins, "tuner holds %zu bandits, need %zu", cc_tuner_bandit_size(tuner),
              first_bandit_id + n_joins);
   cudaStream_t st = as_stream(s);
+  // materialised output: every batch appends behind the rows of the batches before it, so its first row must be known when it
+  // is launched -- that needs the previous batch's count, i.e. no overlap
+  const int depth = h_out_cols ? 1 : 3;
+  constexpr int kMaxDepth = 3;
   cc_chain_result *d_res = nullptr, *h_pin = nullptr;
-  CC_CUDA(cudaMalloc(&d_res, sizeof(cc_chain_result)));
-  cudaError_t e = cudaMallocHost(&h_pin, sizeof(cc_chain_result));
+  cudaEvent_t ev[kMaxDepth] = {nullptr, nullptr, nullptr};
+  size_t arms[kMaxDepth][CC_MAX_JOINS];
+  CC_CUDA(cudaMalloc(&d_res, kMaxDepth * sizeof(cc_chain_result)));
+  cudaError_t e = cudaMallocHost(&h_pin, kMaxDepth * sizeof(cc_chain_result));
+  for (int i = 0; i < kMaxDepth && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
   if (e != cudaSuccess) {
     cudaFree(d_res);
-    set_error("cudaMallocHost: %s", cudaGetErrorString(e));
+    if (h_pin) cudaFreeHost(h_pin);
+    for (auto &x : ev)
+      if (x) cudaEventDestroy(x);
+    set_error("cc_chain_execute_tuned: %s", cudaGetErrorString(e));
+    cudaGetLastError();
     return CC_ERR_NOMEM;
   }
   cc_chain_result total;
   memset(&total, 0, sizeof(total));
   int rc = CC_OK;
-  for (size_t start = 0; start < n_rows || (start == 0 && n_rows == 0); start += batch_rows) {
-    size_t cnt = n_rows - start < batch_rows ? n_rows - start : batch_rows;
+  const size_t n_batches = n_rows ? (n_rows + batch_rows - 1) / batch_rows : 1;
+  // takes the finished batch b off the pipeline: rewards its arms, adds its counters
+  auto retire = [&](size_t b) -> int {
+    const int slot = (int) (b % depth);
+    if (cudaEventSynchronize(ev[slot]) != cudaSuccess) {
+      set_error("cc_chain_execute_tuned: %s", cudaGetErrorString(cudaGetLastError()));
+      return CC_ERR_CUDA;
+    }
+    const cc_chain_result &r = h_pin[slot];
+    const double seconds = (double) r.device_ns * 1e-9;
+    if (seconds > 0)
+      for (size_t l = 0; l < n_joins; ++l) cc_tuner_update_arm(tuner, first_bandit_id + l, arms[slot][l], 2 / seconds / 1e3);  // main.cpp:166
+    total.n_tuples += r.n_tuples;
+    total.digest += r.digest;
+    for (size_t j = 0; j < 3 * n_joins; ++j) total.colsum[j] += r.colsum[j];
+    for (size_t l = 0; l < n_joins; ++l) {
+      total.level_in[l] += r.level_in[l];
+      total.level_steps[l] += r.level_steps[l];
+      total.level_lanes[l] += r.level_lanes[l];
+    }
+    total.device_ns += r.device_ns;
+    if (h_out_cols) total.overflow = total.n_tuples > out_capacity ? 1 : 0;
+    return CC_OK;
+  };
+  size_t retired = 0;
+  for (size_t b = 0; b < n_batches && rc == CC_OK; ++b) {
+    if (b >= (size_t) depth) {  // the slot's previous batch must be off the pipeline before the slot is reused
+      rc = retire(retired++);
+      if (rc != CC_OK) break;
+    }
+    const int slot = (int) (b % depth);
+    const size_t start = b * batch_rows, cnt = n_rows - start < batch_rows ? n_rows - start : batch_rows;
     const int64_t *cols[CC_MAX_JOINS];
     int64_t *outs[3 * CC_MAX_JOINS];
     uint32_t thr[CC_MAX_JOINS];
-    size_t arm[CC_MAX_JOINS];
     for (size_t l = 0; l < n_joins; ++l) {
       cols[l] = h_lhs_cols[l] ? h_lhs_cols[l] + start : nullptr;
-      rc = cc_tuner_select_arm(tuner, first_bandit_id + l, &arm[l]);  // main.cpp:140
+      rc = cc_tuner_select_arm(tuner, first_bandit_id + l, &arms[slot][l]);  // main.cpp:140
       if (rc != CC_OK) break;
-      thr[l] = (uint32_t) (arm[l] > 0xFFFFFFFFull ? 0xFFFFFFFFull : arm[l]);
+      thr[l] = (uint32_t) (arms[slot][l] > 0xFFFFFFFFull ? 0xFFFFFFFFull : arms[slot][l]);
     }
     if (rc != CC_OK) break;
-    size_t used = (size_t) total.n_tuples;
-    size_t room = h_out_cols && out_capacity > used ? out_capacity - used : 0;
+    const size_t used = (size_t) total.n_tuples;  // depth == 1 whenever rows are materialised: every earlier batch is retired
+    const size_t room = h_out_cols && out_capacity > used ? out_capacity - used : 0;
     if (h_out_cols)
       for (size_t j = 0; j < 3 * n_joins; ++j) outs[j] = h_out_cols[j] + (used < out_capacity ? used : out_capacity);
-    rc = cc_chain_execute(h_tables, n_joins, cols, cnt, thr, (h_out_cols && room) ? outs : nullptr, room, d_res, s);
+    rc = cc_chain_execute(h_tables, n_joins, cols, cnt, thr, (h_out_cols && room) ? outs : nullptr, room, d_res + slot, s);
     if (rc != CC_OK) break;
-    if (cudaMemcpyAsync(h_pin, d_res, sizeof(cc_chain_result), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    if (cudaMemcpyAsync(h_pin + slot, d_res + slot, sizeof(cc_chain_result), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaEventRecord(ev[slot], st) != cudaSuccess) {
       set_error("cc_chain_execute_tuned: %s", cudaGetErrorString(cudaGetLastError()));
       rc = CC_ERR_CUDA;
       break;
     }
-    double seconds = (double) h_pin->device_ns * 1e-9;
-    if (seconds > 0)
-      for (size_t l = 0; l < n_joins; ++l) cc_tuner_update_arm(tuner, first_bandit_id + l, arm[l], 2 / seconds / 1e3);  // main.cpp:166
-    total.n_tuples += h_pin->n_tuples;
-    total.digest += h_pin->digest;
-    for (size_t j = 0; j < 3 * n_joins; ++j) total.colsum[j] += h_pin->colsum[j];
-    for (size_t l = 0; l < n_joins; ++l) {
-      total.level_in[l] += h_pin->level_in[l];
-      total.level_steps[l] += h_pin->level_steps[l];
-      total.level_lanes[l] += h_pin->level_lanes[l];
-    }
-    total.device_ns += h_pin->device_ns;
-    if (h_out_cols && (h_pin->overflow || !room)) total.overflow = total.n_tuples > out_capacity ? 1 : 0;
-    if (n_rows == 0) break;
   }
+  while (rc == CC_OK && retired < n_batches) rc = retire(retired++);
+  if (rc != CC_OK) cudaStreamSynchronize(st);
   cudaFree(d_res);
   cudaFreeHost(h_pin);
+  for (auto &x : ev) cudaEventDestroy(x);
   CC_TRY(rc);
   *h_result = total;
   return CC_OK;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kPartThreads) partition_count_kernel(const int
                                                                        unsigned long long *counts, const int *gate, SegIn seg) {
   __shared__ uint32_t s_cnt[kMaxParts];
   if (gate && *gate == 0) return;
-  const int parts = (int) fn.pmask + 1;
+  const int parts = fn.parts();
   for (int i = threadIdx.x; i < parts; i += kPartThreads) s_cnt[i] = 0;
   __syncthreads();
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kPartThreads, 2)
   __shared__ uint16_t s_off[kMaxParts];  // offsets inside the tile (< kPartTile)
   __shared__ unsigned long long s_delta[kMaxParts];  // global base of the partition's run minus its offset in the tile
   __shared__ uint32_t s_warp[kPartThreads / 32];
-  const int parts = (int) fn.pmask + 1;
+  const int parts = fn.parts();
   const size_t ntiles = (n + kPartTile - 1) / kPartTile;
   // complete tiles travel through the TMA buffer (prefetched one tile ahead), ragged ones are loaded directly
   uint32_t phase = 0;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kPartThreads, 2)
         const uint32_t i = (uint32_t) (j * kPartThreads) + threadIdx.x;
         const uint64_t key = s_sorted[i];
         const uint32_t pp = fn(key);
-        int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
+        int64_t *out = PEERS ? dst.p[pp >> fn.sbits] : dst.p[0];
         const unsigned long long d = s_delta[pp];
 #if CCB_SCATTER_ABLATE == 1
         if (d == kDroppedRun + 12345 + key) out[d + i] = (int64_t) key;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kPartThreads, 2)
       for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
         const uint64_t key = s_sorted[i];
         const uint32_t pp = fn(key);
-        int64_t *out = PEERS ? dst.p[pp] : dst.p[0];
+        int64_t *out = PEERS ? dst.p[pp >> fn.sbits] : dst.p[0];
         unsigned long long d = s_delta[pp];
         if (d != kDroppedRun) out[d + i] = (int64_t) key;
       }
@@ -320,32 +320,41 @@ static int launch_scatter(const int64_t *d_keys, size_t n, PartFn fn, const unsi
   return CC_OK;
 }
 
-// tiles of kSegTile rows per partition region (single-pass mode): prefix[p] = first tile of partition p, prefix[parts] = total
-__global__ void partition_seg_prefix_kernel(const unsigned long long *__restrict__ cursors, int parts, unsigned long long cap_rows,
-                                            uint32_t seg_tile, uint32_t *prefix) {
-  __shared__ uint32_t s[kMaxParts];
-  for (int i = threadIdx.x; i < parts; i += blockDim.x) {
-    unsigned long long c = cursors[i] < cap_rows ? cursors[i] : cap_rows;
-    s[i] = (uint32_t) ((c + seg_tile - 1) / seg_tile);
+// tiles of seg_tile rows per partition region: prefix[p] = first tile of segment p (in WALK order), prefix[parts] = total.
+// Any number of segments: one CTA, every thread sums a contiguous chunk, one block scan, every thread writes its chunk.
+__global__ void __launch_bounds__(1024) partition_seg_prefix_kernel(const unsigned long long *__restrict__ cursors, int parts, unsigned long long cap_rows,
+                                                                    uint32_t seg_tile, uint32_t *prefix, SegIn walk) {
+  __shared__ uint32_t s_warp[32];
+  const int per = (parts + (int) blockDim.x - 1) / (int) blockDim.x;
+  const int lo = (int) threadIdx.x * per, hi = lo + per < parts ? lo + per : parts;
+  auto tiles_of = [&](int p) -> uint32_t {
+    const unsigned long long raw = cursors[walk.region((uint32_t) p)];
+    const unsigned long long c = raw < cap_rows ? raw : cap_rows;
+    return (uint32_t) ((c + seg_tile - 1) / seg_tile);
+  };
+  uint32_t mine = 0;
+  for (int p = lo; p < hi; ++p) mine += tiles_of(p);
+  uint32_t incl = warp_incl_scan_u32(mine);
+  if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint32_t x = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+    const uint32_t xi = warp_incl_scan_u32(x);
+    s_warp[threadIdx.x] = xi - x;
+    if (threadIdx.x == 31) prefix[parts] = xi;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < parts; ++i) {
-      uint32_t c = s[i];
-      s[i] = run;
-      run += c;
-    }
-    prefix[parts] = run;
+  uint32_t run = s_warp[threadIdx.x >> 5] + incl - mine;
+  for (int p = lo; p < hi; ++p) {
+    prefix[p] = run;
+    run += tiles_of(p);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < parts; i += blockDim.x) prefix[i] = s[i];
 }
 
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
                             int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg, bool accumulate,
                             int self_part, int64_t *d_self_out, bool sticky_flag) {
-  const int parts = (int) fn.pmask + 1;
+  const int parts = fn.parts();
   if (!accumulate) {
     CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
     // sticky_flag: the kernel only ever ORs into *d_flag, so an overrun reported by an EARLIER call survives until the caller
@@ -359,8 +368,9 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
   if (self_part >= 0 && d_self_out) {
     // one partition goes to a different buffer at the same region offset (the copy-engine exchange: the rows this rank keeps
     // are written straight into its own receive buffer instead of being copied there afterwards)
-    CC_REQUIRE(parts <= kMaxPeers && self_part < parts, "a redirected partition needs at most %d partitions", kMaxPeers);
-    for (int p = 0; p < parts; ++p) dst.p[p] = p == self_part ? d_self_out : d_out;
+    const int owners = fn.obits ? 1 << fn.obits : parts;  // plain function: every partition is an "owner" (sbits == 0)
+    CC_REQUIRE(owners <= kMaxPeers && self_part < owners, "a redirected partition needs at most %d destinations", kMaxPeers);
+    for (int p = 0; p < owners; ++p) dst.p[p] = p == self_part ? d_self_out : d_out;
     CC_TRY(launch_scatter<true>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
   } else {
     CC_TRY(launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
@@ -370,8 +380,8 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
 }
 
 int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,
-                      cudaStream_t st) {
-  partition_seg_prefix_kernel<<<1, 256, 0, st>>>(d_cursors, parts, cap_rows, seg_tile, d_prefix);
+                      cudaStream_t st, SegIn walk) {
+  partition_seg_prefix_kernel<<<1, parts > 256 ? 1024 : 256, 0, st>>>(d_cursors, parts, cap_rows, seg_tile, d_prefix, walk);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -379,7 +389,7 @@ int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned l
 int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long *d_counts, unsigned long long *d_offsets,
                      unsigned long long *d_cursors, int64_t *d_out, cudaStream_t st, cudaEvent_t *after_count, int *gate, SegIn seg,
                      unsigned long long *d_total) {
-  const int parts = (int) fn.pmask + 1;
+  const int parts = fn.parts();
   CC_CUDA(cudaMemsetAsync(d_counts, 0, parts * sizeof(unsigned long long), st));
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   if (blocks == 0) blocks = 1;

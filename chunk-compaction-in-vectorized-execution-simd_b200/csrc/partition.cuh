@@ -11,14 +11,30 @@ constexpr int kMaxParts = 512;
 constexpr int kMaxPeers = 16;  // destination buffers of the peer scatter (GPUs of one NVLink domain)
 static_assert(kMaxParts % kPartThreads == 0, "scan assumes a whole number of bins per thread");
 
-// partition id = ((murmurhash64(key) & pre_mask) >> shift) & pmask
+// partition id = owner * (pmask + 1) + slice  with  slice = ((murmurhash64(key) & pre_mask) >> shift) & pmask  and
+// owner = the high obits bits of the hash (0 when obits == 0): the plain functions have one of the two parts, the FUSED
+// function of the partitioned join (pjoin.cu) both -- a sender groups its keys by (owner GPU, table slice of that owner) in
+// one pass, so that the owner never has to partition what it receives.
 struct PartFn {
   uint64_t pre_mask;
   uint32_t shift;
   uint32_t pmask;
+  uint32_t obits = 0;  // log2 of the number of owners
+  uint32_t sbits = 0;  // log2 (pmask + 1), only needed when obits > 0
   __host__ __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
-    uint64_t h = murmurhash64(key) & pre_mask;
-    return shift >= 64 ? 0u : ((uint32_t) (h >> shift) & pmask);
+    const uint64_t hh = murmurhash64(key);
+    const uint64_t h = hh & pre_mask;
+    const uint32_t slice = shift >= 64 ? 0u : ((uint32_t) (h >> shift) & pmask);
+    return obits ? (((uint32_t) (hh >> (64 - obits))) << sbits) | slice : slice;
+  }
+  __host__ __device__ __forceinline__ int parts() const { return (int) ((pmask + 1u) << obits); }
+  // owner x table slice: owner = high log2_owners hash bits, slice = high log2_slices bits of the home slot / bucket in a table
+  // of 2^log2_slots entries (every owner's table has the same size)
+  static PartFn owner_and_slice(int log2_owners, uint64_t table_mask, int log2_slots, int log2_slices) {
+    PartFn f = log2_slices > 0 ? slot_bits(table_mask, log2_slots, log2_slices) : PartFn{0, 64, 0};
+    f.obits = (uint32_t) log2_owners;
+    f.sbits = (uint32_t) log2_slices;
+    return f;
   }
   // multi-GPU owner: the high log2p bits of the hash
   static PartFn high_bits(int log2p) {
@@ -41,10 +57,20 @@ struct PartFn {
 // Segmented INPUT column (the receive buffer of the copy-engine exchange, parallel.py): segment s holds counts[s] valid rows
 // at keys + s * cap, cap a multiple of kPartTile; the kernels then walk n = segments * cap rows and skip the slack.
 // cap == 0: plain dense input.
+// inner > 0: the segments are WALKED in an order that differs from their order in memory -- segment p of the walk is region
+//   r = (p % inner) * outer_stride + p / inner   (rows at keys + r * cap, fill counts[r]).  The receive arena of the partitioned
+//   join is laid out [piece][sender][slice] and probed slice by slice: inner = pieces * senders, outer_stride = slices allocated.
+// presliced: the regions already are table slices (the sender partitioned by owner AND slice): probe them as they are.
 struct SegIn {
   const unsigned long long *counts = nullptr;
   unsigned long long cap = 0;
   int segments = 0;
+  int inner = 0;
+  int outer_stride = 0;
+  bool presliced = false;
+  __host__ __device__ __forceinline__ uint32_t region(uint32_t p) const {
+    return inner ? (p % (uint32_t) inner) * (uint32_t) outer_stride + p / (uint32_t) inner : p;
+  }
 };
 
 // histogram + offsets + scatter on `st`; d_counts/d_offsets/d_cursors hold P entries each
@@ -60,10 +86,11 @@ int partition_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long l
 int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors,
                             int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg = SegIn(),
                             bool accumulate = false, int self_part = -1, int64_t *d_self_out = nullptr, bool sticky_flag = false);
+// (a fused owner x slice function: self_part is the OWNER whose regions go to d_self_out)
 // accumulate: keep cursors / flag of earlier calls (the regions fill up over several inputs)
 // d_prefix[0 .. parts] = exclusive prefix of ceil(min(d_cursors[p], cap_rows) / seg_tile) (the probe kernel's tile directory)
 int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,
-                      cudaStream_t st);
+                      cudaStream_t st, SegIn walk = SegIn());  // walk.inner > 0: prefix in walk order (d_cursors indexed by region)
 
 // probe a SEGMENTED key column (probe_batch.cu); accumulate: keep the running match count / output position of earlier calls
 int probe_segmented_device(const cc_ht *ht, const int64_t *d_keys, SegIn seg, int64_t *d_out_key, int64_t *d_out_payload, size_t cap,

@@ -3,19 +3,26 @@
 //
 // Both sides of an equi-join are partitioned by owner = murmurhash64(key) >> (64 - log2 P) (high hash bits, independent of the
 // low bits that address the owner's table) and every rank builds / probes its own table with the single-GPU kernels
-// (linear_probing_ht.cpp:4-115 / chaining_ht.cpp:4-136 per rank).  The exchange is made of four device-side pieces:
-//   * partition_scatter_kernel (single pass, fixed regions): groups a sub-batch by owner in a local send buffer; the rows this
-//     rank keeps go straight into its own receive buffer;
-//   * copy engines: region p travels as ONE cudaMemcpyAsync into slot [this rank] of owner p's receive buffer (CUDA-IPC mapping of
-//     peer memory over NVLink 5 / NVSwitch), on several copy streams, without occupying an SM;
-//   * pj_signal_kernel: stores the region's row count and an epoch flag into the owner's control block over NVLink, behind the
-//     copies in stream order ("rows of shuffle k from sender s have landed");
-//   * pj_wait_kernel: the owner's main stream spins (bounded) on its own flags until every sender's epoch has arrived; after the
-//     probe pj_consumed_kernel tells every sender that the buffer may be refilled (a sender waits for that before shuffle k + 3).
-// So the host never learns a count and never blocks: a probe call enqueues  P(0) P(1) W(0) L(0) C(0) P(2) W(1) L(1) C(1) ...
-// (P = owner partition + copies, W = wait, L = slice partition + probe of the received sub-batch, C = consumed) and returns.
-// The host's only job is the control plane at create / destroy time (exchange of the IPC handles and sizes through the
-// caller's cc_comm callbacks: MPI, torch.distributed, or the fork + shared-memory communicator of host/simd_compaction.hpp).
+// (linear_probing_ht.cpp:4-115 / chaining_ht.cpp:4-136 per rank).
+//
+// The probe side is partitioned ONCE, on the sender: partition_scatter_kernel groups a piece of the probe keys by
+// (owner GPU, table slice of that owner) -- every rank's table has the same size, so a sender knows the slice a key will fall
+// into on its owner.  What an owner receives is therefore already grouped by L2-sized table slices and is probed as it lies:
+// per key the SMs do one scatter and one probe, exactly what a single GPU does for the same keys (the round-1 pipeline did an
+// owner partition on the sender AND a slice partition on the receiver: 2x the SM work per key, scaling efficiency 0.53).
+// The exchange itself is made of device-side pieces only:
+//   * copy engines: the regions of owner o travel as ONE cudaMemcpyAsync into slot [piece][this rank] of o's receive arena
+//     (CUDA-IPC mapping of peer memory over NVLink 5 / NVSwitch), on several copy streams, without occupying an SM; the rows a
+//     rank keeps are written straight into its own arena by the scatter kernel;
+//   * pj_signal_kernel: stores the regions' row counts and an epoch flag into the owner's control block over NVLink, behind the
+//     copies in stream order ("piece b of this step from sender s has landed");
+//   * pj_wait_kernel: the owner's stream spins (bounded) on its own flags until every piece of every sender has arrived, then
+//     ONE probe walks the arena slice by slice (all pieces and senders of slice 0, then slice 1, ...: the table is streamed
+//     from HBM once per step); pj_consumed_kernel then tells every sender that the arena may be refilled (two arenas alternate
+//     between steps, so the copies of step t + 1 land while step t is still being probed).
+// The host never learns a count and never blocks: a probe call enqueues  F(0) F(1) .. F(B-1) W PROBE C  and returns.  The host's
+// only job is the control plane at create / destroy time (exchange of the IPC handles and sizes through the caller's cc_comm
+// callbacks: MPI, torch.distributed, or the fork + shared-memory communicator of host/simd_compaction.hpp).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -25,21 +32,42 @@
 
 namespace ccb {
 
-constexpr int kPjBuffers = 3;       // rotating receive / send buffers
+constexpr int kPjArenas = 2;        // receive arenas, alternating between steps
+constexpr int kPjSendSlots = 3;     // rotating send buffers (one piece each)
 constexpr int kPjCopyStreams = 4;   // one stream drives one copy engine at a time
+constexpr int kPjMaxPieces = 16;
 constexpr unsigned long long kPjSpinNs = 20ull * 1000 * 1000 * 1000;  // a wait gives up after 20 s (a peer died): error bit, no hang
+constexpr size_t kPjSliceBytes = 32u << 20;                           // target table bytes per slice (profiles/r1_sweep_slices.txt)
+constexpr size_t kPjSliceMinTable = 96u << 20;                        // smaller tables are probed directly (they live in L2 anyway)
 
-// control block at the head of every rank's exchange allocation; written by PEERS over NVLink
-struct PjCtrl {
-  unsigned long long counts[kPjBuffers][kMaxPeers];    // [b][s]: rows sender s delivered into buffer b
-  unsigned long long ready[kPjBuffers][kMaxPeers];     // [b][s]: epoch of the last shuffle sender s delivered into buffer b
-  unsigned long long consumed[kPjBuffers][kMaxPeers];  // [b][r]: epoch of the last shuffle receiver r has finished reading from ITS buffer b (of OUR rows)
+// Control block at the head of every rank's exchange allocation, written by PEERS over NVLink.  Geometry-independent layout
+// (strides are the ALLOCATED piece / slice counts): flag index (arena * Ba + piece) * P + sender, count index that * Sa + slice.
+struct PjLayout {
+  int P = 1, Ba = 1, Sa = 1;      // ranks, pieces allocated, slices allocated
+  unsigned long long cap = 0;     // rows per region
+  size_t ready_off = 0, consumed_off = 0, counts_off = 0, data_off = 0, total = 0;
+  __host__ __device__ size_t flag_index(int arena, int piece, int sender) const { return ((size_t) arena * Ba + piece) * P + sender; }
+  __host__ __device__ size_t region_index(int piece, int sender, int slice) const { return ((size_t) piece * P + sender) * Sa + slice; }
+  size_t arena_rows() const { return (size_t) Ba * P * Sa * cap; }
+  void finish() {
+    auto up = [](size_t x) { return (x + 4095) / 4096 * 4096; };
+    ready_off = 0;
+    consumed_off = up(ready_off + (size_t) kPjArenas * Ba * P * 8);
+    counts_off = up(consumed_off + (size_t) kPjArenas * kMaxPeers * 8);
+    data_off = up(counts_off + (size_t) kPjArenas * Ba * P * Sa * 8);
+    total = data_off + (size_t) kPjArenas * arena_rows() * 8;
+  }
 };
-constexpr size_t kPjCtrlBytes = (sizeof(PjCtrl) + 4095) / 4096 * 4096;
 
 struct PjPeers {
-  PjCtrl *ctrl[kMaxPeers];
+  unsigned char *base[kMaxPeers];
 };
+
+static int log2_floor_pj(size_t x) {
+  int l = 0;
+  while ((x >> l) > 1) ++l;
+  return l;
+}
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) {
   unsigned long long v;
@@ -50,57 +78,67 @@ __device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long 
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// thread p < world: tell owner p that this rank's region of shuffle `epoch` (buffer b) has landed, with its row count
-__global__ void pj_signal_kernel(PjPeers peers, int world, int rank, int b, const unsigned long long *__restrict__ d_counts, unsigned long long cap,
+// block o < P: tell owner o that this rank's regions of (arena, piece) have landed -- S row counts, then the epoch flag
+__global__ void pj_signal_kernel(PjPeers peers, PjLayout lay, int rank, int arena, int piece, int S, const unsigned long long *__restrict__ d_counts,
                                  unsigned long long epoch) {
-  const int p = threadIdx.x;
-  if (p >= world) return;
-  unsigned long long c = d_counts[p];
-  if (c > cap) c = cap;  // an overrun region was clamped by the scatter kernel (and flagged)
-  peers.ctrl[p]->counts[b][rank] = c;
+  const int o = blockIdx.x;
+  unsigned long long *counts = reinterpret_cast<unsigned long long *>(peers.base[o] + lay.counts_off) +
+                               ((size_t) arena * lay.Ba * lay.P * lay.Sa + lay.region_index(piece, rank, 0));
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    unsigned long long c = d_counts[(size_t) o * S + s];
+    counts[s] = c < lay.cap ? c : lay.cap;  // an overrun region was clamped by the scatter kernel (and flagged)
+  }
   __threadfence_system();
-  st_sys_u64(&peers.ctrl[p]->ready[b][rank], epoch);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    st_sys_u64(reinterpret_cast<unsigned long long *>(peers.base[o] + lay.ready_off) + lay.flag_index(arena, piece, rank), epoch);
 }
 
-// thread s < world: wait until flags[s] >= epoch (flags live in THIS rank's memory, peers write them); bounded
-__global__ void pj_wait_kernel(const unsigned long long *flags, int world, unsigned long long epoch, int *d_err) {
-  const int s = threadIdx.x;
-  if (s >= world) return;
-  const unsigned long long t0 = globaltimer_ns();
-  while (ld_sys_u64(flags + s) < epoch) {
-    __nanosleep(200);
-    if (globaltimer_ns() - t0 > kPjSpinNs) {
-      atomicOr(d_err, 1);
-      return;
+// thread i < n: wait until flags[i] >= epoch (the flags live in THIS rank's memory, peers write them); bounded
+__global__ void pj_wait_kernel(const unsigned long long *flags, int n, unsigned long long epoch, int *d_err) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_sys_u64(flags + i) < epoch) {
+      __nanosleep(200);
+      if (globaltimer_ns() - t0 > kPjSpinNs) {
+        atomicOr(d_err, 1);
+        return;
+      }
     }
   }
 }
 
-// thread s < world: tell sender s that this rank has finished reading buffer b of shuffle `epoch`
-__global__ void pj_consumed_kernel(PjPeers peers, int world, int rank, int b, unsigned long long epoch) {
+// thread s < P: tell sender s that this rank has finished reading its arena `arena` (use `epoch`)
+__global__ void pj_consumed_kernel(PjPeers peers, PjLayout lay, int rank, int arena, unsigned long long epoch) {
   const int s = threadIdx.x;
-  if (s >= world) return;
-  st_sys_u64(&peers.ctrl[s]->consumed[b][rank], epoch);
+  if (s >= lay.P) return;
+  st_sys_u64(reinterpret_cast<unsigned long long *>(peers.base[s] + lay.consumed_off) + (size_t) arena * kMaxPeers + rank, epoch);
 }
 
-// append the valid rows of a segmented column (segment s: counts[s] rows at src + s * cap) to dst[*cursor ...]; rows beyond
-// dst_cap are dropped (the cursor still counts them: the host sees the overflow)
+// append the valid rows of `segments` regions (region q: counts[q * count_stride] rows at src + q * row_stride) to
+// dst[*cursor ...]; rows beyond dst_cap are dropped (the cursor still counts them: the host sees the overflow)
 __global__ void pj_compact_kernel(const int64_t *__restrict__ src, const unsigned long long *__restrict__ counts, unsigned long long cap, int segments,
-                                  int64_t *__restrict__ dst, unsigned long long dst_cap, const unsigned long long *__restrict__ cursor) {
+                                  size_t row_stride, size_t count_stride, int64_t *__restrict__ dst, unsigned long long dst_cap,
+                                  const unsigned long long *__restrict__ cursor) {
   const unsigned long long base0 = *cursor;
   const size_t stride = (size_t) gridDim.x * blockDim.x;
-  for (int s = 0; s < segments; ++s) {
-    unsigned long long before = base0;
-    for (int t = 0; t < s; ++t) before += counts[t] < cap ? counts[t] : cap;
-    const unsigned long long c = counts[s] < cap ? counts[s] : cap;
+  unsigned long long before = base0;
+  for (int q = 0; q < segments; ++q) {
+    const unsigned long long raw = counts[(size_t) q * count_stride];
+    const unsigned long long c = raw < cap ? raw : cap;
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < c; i += stride)
-      if (before + i < dst_cap) dst[before + i] = src[(size_t) s * cap + i];
+      if (before + i < dst_cap) dst[before + i] = src[(size_t) q * row_stride + i];
+    before += c;
   }
 }
-__global__ void pj_advance_kernel(const unsigned long long *__restrict__ counts, unsigned long long cap, int segments, unsigned long long *cursor) {
+__global__ void pj_advance_kernel(const unsigned long long *__restrict__ counts, unsigned long long cap, int segments, size_t count_stride,
+                                  unsigned long long *cursor) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     unsigned long long t = 0;
-    for (int s = 0; s < segments; ++s) t += counts[s] < cap ? counts[s] : cap;
+    for (int q = 0; q < segments; ++q) {
+      const unsigned long long raw = counts[(size_t) q * count_stride];
+      t += raw < cap ? raw : cap;
+    }
     *cursor += t;
   }
 }
@@ -118,22 +156,27 @@ using namespace ccb;
 
 struct cc_pjoin {
   cc_comm comm;
-  int world = 1, rank = 0, log2p = 0, kind = CC_HT_LP, n_sub = 1, device = 0;
-  size_t max_rows = 0;            // rows per shuffle (one sub-batch)
-  unsigned long long cap = 0;     // rows per (sender, owner) region
-  unsigned char *block = nullptr;                // own exchange allocation: PjCtrl | kPjBuffers x world x cap rows
-  unsigned char *peer_block[kMaxPeers] = {};     // every rank's allocation in this address space (own pointer at [rank])
-  int64_t *send[kPjBuffers] = {};
-  unsigned long long *d_counts = nullptr;        // [kPjBuffers][kMaxParts... world] cursors of the owner partition
-  int *d_flag = nullptr, *d_err = nullptr;       // sticky region-overrun flag, wait-timeout flag
+  int world = 1, rank = 0, log2p = 0, kind = CC_HT_LP, device = 0;
+  int pieces = 1;                 // pieces (sub-batches) of one probe call
+  int slices = 1, log2s = 0;      // table slices the probe side is grouped by on the sender (1: the table lives in L2)
+  size_t max_rows = 0;            // rows per piece
+  PjLayout lay;
+  unsigned char *block = nullptr;              // own exchange allocation: flags | counts | kPjArenas arenas
+  unsigned char *peer_block[kMaxPeers] = {};   // every rank's allocation in this address space (own pointer at [rank])
+  int64_t *send[kPjSendSlots] = {};            // [owner][slice][cap]
+  unsigned long long *d_counts = nullptr;      // [kPjSendSlots][P * Sa] fill counts of the scatter
+  int *d_flag = nullptr, *d_err = nullptr;     // sticky region-overrun flag, wait-timeout flag
   cudaStream_t cs[kPjCopyStreams] = {};
-  cudaEvent_t parted[kPjBuffers] = {}, copied[kPjBuffers] = {}, gate = nullptr, joined[kPjCopyStreams] = {};
-  unsigned long long shuffles = 0;               // global shuffle counter: epoch of shuffle k is k + 1, its buffer k % kPjBuffers
+  cudaEvent_t parted[kPjSendSlots] = {}, copied[kPjSendSlots] = {}, gate = nullptr, joined[kPjCopyStreams] = {};
+  unsigned long long sends = 0;                // pieces sent so far (send slot = sends % kPjSendSlots)
+  unsigned long long uses = 0;                 // arena uses so far (arena = uses % kPjArenas, its epoch = uses / kPjArenas + 1)
   cc_ht *table = nullptr;
-  size_t n_build_total = 0;
+  size_t n_build_total = 0, table_slots = 0;
 
-  PjCtrl *ctrl(int r) const { return reinterpret_cast<PjCtrl *>(peer_block[r]); }
-  int64_t *data(int r, int b) const { return reinterpret_cast<int64_t *>(peer_block[r] + kPjCtrlBytes) + (size_t) b * world * cap; }
+  int64_t *arena(int r, int a) const { return reinterpret_cast<int64_t *>(peer_block[r] + lay.data_off) + (size_t) a * lay.arena_rows(); }
+  unsigned long long *counts(int a) const {
+    return reinterpret_cast<unsigned long long *>(block + lay.counts_off) + (size_t) a * lay.Ba * lay.P * lay.Sa;
+  }
 };
 
 namespace {
@@ -150,67 +193,58 @@ namespace {
 
 PjPeers peers_of(const cc_pjoin *j) {
   PjPeers p;
-  for (int r = 0; r < kMaxPeers; ++r) p.ctrl[r] = r < j->world ? j->ctrl(r) : nullptr;
+  for (int r = 0; r < kMaxPeers; ++r) p.base[r] = r < j->world ? j->peer_block[r] : nullptr;
   return p;
 }
 
-// first half of shuffle k: owner partition on `st`, block copies + signal on the copy streams.  Returns k.
-int shuffle_start(cc_pjoin *j, const int64_t *d_keys, size_t n, cudaStream_t st, unsigned long long *out_k) {
-  CC_REQUIRE(n <= j->max_rows, "%zu rows exceed the %zu rows per shuffle this join was sized for", n, j->max_rows);
-  const unsigned long long k = j->shuffles++;
-  const int b = (int) (k % kPjBuffers);
+// Sends one piece: the keys are grouped by (owner, slice) with `S` slices per owner (S == 1: by owner only) into a send slot,
+// owner o's regions are copied into [piece][this rank] of o's arena `arena`, then o is signalled with epoch `epoch`.
+// first_of_use: the arena is about to be refilled for the first time in this use -- wait until every owner has consumed its
+// previous use.
+int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, int arena, int piece, unsigned long long epoch, bool first_of_use,
+               cudaStream_t st) {
   const int P = j->world;
-  unsigned long long *counts = j->d_counts + (size_t) b * kMaxPeers;
-  if (k >= (unsigned long long) kPjBuffers) PJ_CUDA(cudaStreamWaitEvent(st, j->copied[b], 0));  // the copies of shuffle k - 3 have left send[b]
-  // the rows this rank keeps go straight into slot [rank] of its own receive buffer (same region offset rank * cap)
-  CC_TRY(partition_single_device(d_keys, n, PartFn::high_bits(j->log2p), j->cap, counts, j->d_flag, 0, nullptr, j->send[b], st, SegIn(), false,
-                                 P > 1 ? j->rank : -1, P > 1 ? j->data(j->rank, b) : nullptr, /*sticky_flag=*/true));
-  if (P == 1) {  // a single rank: the send buffer IS the receive column
-    PJ_CUDA(cudaMemcpyAsync(j->data(0, b), j->send[b], (size_t) j->cap * 8, cudaMemcpyDeviceToDevice, st));
+  const PjLayout &lay = j->lay;
+  const unsigned long long k = j->sends++;
+  const int slot = (int) (k % kPjSendSlots);
+  unsigned long long *counts = j->d_counts + (size_t) slot * P * lay.Sa;
+  if (k >= (unsigned long long) kPjSendSlots) PJ_CUDA(cudaStreamWaitEvent(st, j->copied[slot], 0));  // the copies of piece k - 3 have left the slot
+  const PartFn fn = S > 1 ? PartFn::owner_and_slice(j->log2p, j->table_slots - 1, log2_floor_pj(j->table_slots), log2s)
+                          : PartFn::high_bits(j->log2p);
+  // Region q = owner * S + slice sits at q * cap in the send slot.  The rows this rank keeps go straight into its own arena:
+  // there the same region lives at region_index(piece, rank, slice) * cap, so the redirect pointer is shifted accordingly.
+  int64_t *self = j->arena(j->rank, arena) + lay.region_index(piece, j->rank, 0) * lay.cap - (size_t) j->rank * S * lay.cap;
+  if (S != lay.Sa) {
+    // the arena's slice stride is the allocated one: a geometry with fewer slices (the build side: S == 1) cannot be written in
+    // place by the scatter kernel, it is copied like a peer's
+    self = nullptr;
   }
-  PJ_CUDA(cudaEventRecord(j->parted[b], st));
+  CC_TRY(partition_single_device(d_keys, n, fn, lay.cap, counts, j->d_flag, 0, nullptr, j->send[slot], st, SegIn(), false,
+                                 (self && P > 1) ? j->rank : -1, (self && P > 1) ? self : nullptr, /*sticky_flag=*/true));
+  PJ_CUDA(cudaEventRecord(j->parted[slot], st));
   cudaStream_t c0 = j->cs[0];
-  PJ_CUDA(cudaStreamWaitEvent(c0, j->parted[b], 0));
-  if (k >= (unsigned long long) kPjBuffers) {
-    // every owner must have finished reading what shuffle k - 3 put into its buffer b before it is refilled
-    pj_wait_kernel<<<1, 32, 0, c0>>>(&j->ctrl(j->rank)->consumed[b][0], P, k - kPjBuffers + 1, j->d_err);
+  PJ_CUDA(cudaStreamWaitEvent(c0, j->parted[slot], 0));
+  if (first_of_use && epoch > 1) {
+    pj_wait_kernel<<<1, 32, 0, c0>>>(reinterpret_cast<unsigned long long *>(j->block + lay.consumed_off) + (size_t) arena * kMaxPeers, P, epoch - 1, j->d_err);
     CC_CHECK_LAUNCH();
   }
   PJ_CUDA(cudaEventRecord(j->gate, c0));
   for (int s = 1; s < kPjCopyStreams; ++s) PJ_CUDA(cudaStreamWaitEvent(j->cs[s], j->gate, 0));
-  const size_t bytes = (size_t) j->cap * 8;
-  for (int i = 1; i < P; ++i) {
-    const int p = (j->rank + i) % P;  // stagger the destinations so that the ranks do not all hit the same peer at once
-    PJ_CUDA(cudaMemcpyAsync(j->data(p, b) + (size_t) j->rank * j->cap, j->send[b] + (size_t) p * j->cap, bytes, cudaMemcpyDeviceToDevice,
-                            j->cs[(i - 1) % kPjCopyStreams]));
+  const size_t bytes = (size_t) S * lay.cap * 8;
+  int n_copy = 0;
+  for (int i = 0; i < P; ++i) {
+    const int o = (j->rank + i) % P;  // stagger the destinations so that the ranks do not all hit the same peer at once
+    if (o == j->rank && self && P > 1) continue;  // written in place by the scatter kernel
+    PJ_CUDA(cudaMemcpyAsync(j->arena(o, arena) + lay.region_index(piece, j->rank, 0) * lay.cap, j->send[slot] + (size_t) o * S * lay.cap, bytes,
+                            cudaMemcpyDeviceToDevice, j->cs[n_copy++ % kPjCopyStreams]));
   }
   for (int s = 1; s < kPjCopyStreams; ++s) {
     PJ_CUDA(cudaEventRecord(j->joined[s], j->cs[s]));
     PJ_CUDA(cudaStreamWaitEvent(c0, j->joined[s], 0));
   }
-  pj_signal_kernel<<<1, 32, 0, c0>>>(peers_of(j), P, j->rank, b, counts, j->cap, k + 1);
+  pj_signal_kernel<<<P, 128, 0, c0>>>(peers_of(j), lay, j->rank, arena, piece, S, counts, epoch);
   CC_CHECK_LAUNCH();
-  PJ_CUDA(cudaEventRecord(j->copied[b], c0));
-  *out_k = k;
-  return CC_OK;
-}
-
-// second half: `st` waits until every sender's rows of shuffle k have landed; the receive column is then data(rank, b) with
-// world segments of cap rows and the counts in the control block
-int shuffle_finish(cc_pjoin *j, unsigned long long k, cudaStream_t st, const int64_t **col, SegIn *seg) {
-  const int b = (int) (k % kPjBuffers);
-  pj_wait_kernel<<<1, 32, 0, st>>>(&j->ctrl(j->rank)->ready[b][0], j->world, k + 1, j->d_err);
-  CC_CHECK_LAUNCH();
-  *col = j->data(j->rank, b);
-  seg->counts = &j->ctrl(j->rank)->counts[b][0];
-  seg->cap = j->cap;
-  seg->segments = j->world;
-  return CC_OK;
-}
-
-int shuffle_consumed(cc_pjoin *j, unsigned long long k, cudaStream_t st) {
-  pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), j->world, j->rank, (int) (k % kPjBuffers), k + 1);
-  CC_CHECK_LAUNCH();
+  PJ_CUDA(cudaEventRecord(j->copied[slot], c0));
   return CC_OK;
 }
 
@@ -252,14 +286,14 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   CC_REQUIRE(comm->rank >= 0 && comm->rank < comm->world, "rank %d out of range", comm->rank);
   CC_REQUIRE(kind == CC_HT_LP || kind == CC_HT_CHAIN, "unknown table kind %d", kind);
   CC_REQUIRE(n_build_local == 0 || d_build_keys, "d_build_keys is NULL");
-  CC_REQUIRE(n_sub >= 1 && n_sub <= 64, "n_sub must be in [1, 64]");
+  CC_REQUIRE(n_sub >= 1 && n_sub <= kPjMaxPieces, "n_sub must be in [1, %d]", kPjMaxPieces);
   cudaStream_t st = as_stream(s);
   cc_pjoin *j = new cc_pjoin();
   j->comm = *comm;
   j->world = comm->world;
   j->rank = comm->rank;
   j->kind = kind;
-  j->n_sub = n_sub;
+  j->pieces = n_sub;
   while ((1 << j->log2p) < j->world) ++j->log2p;
   cudaGetDevice(&j->device);
   const int P = j->world;
@@ -268,8 +302,7 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     pj_release(j);
     return code;
   };
-  // ---- sizes: every rank learns every rank's build rows; one shuffle moves at most max_rows rows per rank
-  std::vector<unsigned long long> sizes(P, 0);
+  // ---- sizes: every rank learns every rank's build rows and probe rows per call
   unsigned long long mine[2] = {(unsigned long long) n_build_local, (unsigned long long) max_probe_rows};
   std::vector<unsigned long long> all(2 * (size_t) P, 0);
   if (comm->allgather(comm->user, mine, all.data(), sizeof(mine)) != 0) {
@@ -284,20 +317,43 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   }
   j->n_build_total = (size_t) n_total;
   j->max_rows = std::max<size_t>(1, (size_t) ((max_probe + n_sub - 1) / n_sub));
-  const unsigned long long per = (j->max_rows + P - 1) / P;
-  j->cap = (per + per / 32 + 2 * (unsigned long long) kPartTile + kPartTile - 1) / kPartTile * kPartTile;
-  // ---- exchange memory + IPC mapping of every peer's block
-  const size_t data_bytes = (size_t) kPjBuffers * P * j->cap * 8;
-  cudaError_t e = cudaMalloc(&j->block, kPjCtrlBytes + data_bytes);
-  if (e == cudaSuccess) e = cudaMemset(j->block, 0, kPjCtrlBytes);
-  for (int b = 0; b < kPjBuffers && e == cudaSuccess; ++b) e = cudaMalloc(&j->send[b], (size_t) P * j->cap * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&j->d_counts, (size_t) kPjBuffers * kMaxPeers * sizeof(unsigned long long));
+  // ---- every rank's table gets the SAME size: the reference's rule on the GLOBAL key count (linear_probing_ht.cpp:5-6: pow2 >=
+  // 4n; chaining_ht.cpp:5-6: pow2 >= 2n) divided by the ranks, with headroom for an uneven hash partition (LP: at most half full
+  // as long as no rank owns more than twice its share) -- a sender must know the slice a key falls into on its owner
+  size_t slots = 1;
+  const size_t per_key = kind == CC_HT_LP ? 4 : 2;
+  while (slots < per_key * (size_t) n_total) slots <<= 1;
+  slots = std::max<size_t>(1, slots / P);  // (one rank: exactly the reference's rule)
+  j->table_slots = slots;
+  // table slices: L2-sized, a power of two, at most kMaxParts / P (the scatter kernel ranks P * S partitions per tile)
+  const size_t table_bytes = kind == CC_HT_LP ? slots * 8 : slots * 8 + (size_t) (n_total / P) * 8;
+  int S = 1, log2s = 0;
+  if (table_bytes >= kPjSliceMinTable && slots <= (1ull << 32)) {
+    while ((size_t) S * kPjSliceBytes < table_bytes && S * 2 * P <= kMaxParts && (size_t) S * 2 <= slots) {
+      S *= 2;
+      ++log2s;
+    }
+  }
+  j->slices = S;
+  j->log2s = log2s;
+  // ---- exchange geometry
+  PjLayout &lay = j->lay;
+  lay.P = P;
+  lay.Ba = n_sub;
+  lay.Sa = S;
+  const unsigned long long per = (j->max_rows + (size_t) P * S - 1) / ((size_t) P * S);
+  lay.cap = (per + per / 32 + 2 * (unsigned long long) kPartTile + kPartTile - 1) / kPartTile * kPartTile;
+  lay.finish();
+  cudaError_t e = cudaMalloc(&j->block, lay.total);
+  if (e == cudaSuccess) e = cudaMemset(j->block, 0, lay.data_off);
+  for (int b = 0; b < kPjSendSlots && e == cudaSuccess; ++b) e = cudaMalloc(&j->send[b], (size_t) P * S * lay.cap * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&j->d_counts, (size_t) kPjSendSlots * P * S * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&j->d_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&j->d_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(j->d_flag, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(j->d_err, 0, sizeof(int));
   for (int i = 0; i < kPjCopyStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&j->cs[i], cudaStreamNonBlocking);
-  for (int i = 0; i < kPjBuffers && e == cudaSuccess; ++i) {
+  for (int i = 0; i < kPjSendSlots && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&j->parted[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->copied[i], cudaEventDisableTiming);
   }
@@ -305,7 +361,7 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->gate, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
-    set_error("cc_pjoin_create: %s", cudaGetErrorString(e));
+    set_error("cc_pjoin_create: %s (exchange memory: %zu bytes)", cudaGetErrorString(e), lay.total);
     cudaGetLastError();
     return fail(e == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA);
   }
@@ -328,8 +384,9 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     }
   }
   if (comm->barrier(comm->user) != 0) return fail(CC_ERR_INVALID);  // every control block is zeroed and mapped before anyone signals
-  // ---- build side: shuffle it piece by piece, append what arrives to a dense column, build the local table
-  const size_t pieces = (size_t) ((max_local + j->max_rows - 1) / j->max_rows);
+  // ---- build side: exchanged piece by piece by owner only (one region per owner), appended to a dense column
+  const size_t piece_rows = std::max<size_t>(1, (size_t) ((lay.cap - 2 * (unsigned long long) kPartTile) * 32 / 33) * P);  // its owner shares fit a region
+  const size_t pieces = (size_t) ((max_local + piece_rows - 1) / piece_rows);
   const size_t build_cap = (size_t) (n_total / P + n_total / P / 4 + (1u << 16));
   int64_t *d_build = nullptr;
   unsigned long long *d_cursor = nullptr;
@@ -342,22 +399,28 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     cudaGetLastError();
     return fail(CC_ERR_NOMEM);
   }
+  const size_t saved_max = j->max_rows;
+  j->max_rows = piece_rows;
   for (size_t piece = 0; piece < pieces && rc == CC_OK; ++piece) {
-    const size_t off = std::min(n_build_local, piece * j->max_rows), cnt = std::min(j->max_rows, n_build_local - off);
-    unsigned long long k = 0;
-    rc = shuffle_start(j, cnt ? d_build_keys + off : nullptr, cnt, st, &k);
-    const int64_t *col = nullptr;
-    SegIn seg;
-    if (rc == CC_OK) rc = shuffle_finish(j, k, st, &col, &seg);
-    if (rc == CC_OK) {
-      pj_compact_kernel<<<sm_count() * 4, 256, 0, st>>>(col, seg.counts, seg.cap, seg.segments, d_build, build_cap, d_cursor);
-      note_launch();
-      pj_advance_kernel<<<1, 32, 0, st>>>(seg.counts, seg.cap, seg.segments, d_cursor);
-      note_launch();
-      if (cudaGetLastError() != cudaSuccess) rc = CC_ERR_CUDA;
-    }
-    if (rc == CC_OK) rc = shuffle_consumed(j, k, st);
+    const size_t off = std::min(n_build_local, piece * piece_rows), cnt = std::min(piece_rows, n_build_local - off);
+    const int arena = (int) (j->uses % kPjArenas);
+    const unsigned long long epoch = j->uses / kPjArenas + 1;
+    ++j->uses;
+    rc = send_piece(j, cnt ? d_build_keys + off : nullptr, cnt, /*S=*/1, 0, arena, /*piece=*/0, epoch, true, st);
+    if (rc != CC_OK) break;
+    pj_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, 0, 0), P, epoch, j->d_err);
+    note_launch();
+    // one region per sender: region_index(0, sender, 0) = sender * Sa
+    pj_compact_kernel<<<sm_count() * 4, 256, 0, st>>>(j->arena(j->rank, arena), j->counts(arena), lay.cap, P, (size_t) lay.Sa * lay.cap, (size_t) lay.Sa,
+                                                    d_build, build_cap, d_cursor);
+    note_launch();
+    pj_advance_kernel<<<1, 32, 0, st>>>(j->counts(arena), lay.cap, P, (size_t) lay.Sa, d_cursor);
+    note_launch();
+    pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), lay, j->rank, arena, epoch);
+    note_launch();
+    if (cudaGetLastError() != cudaSuccess) rc = CC_ERR_CUDA;
   }
+  j->max_rows = saved_max;
   unsigned long long n_owned = 0;
   int h_flag = 0, h_err = 0;
   if (rc == CC_OK) {
@@ -372,7 +435,8 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     }
   }
   // every rank learns whether EVERY rank's build exchange went through, so that all of them fail (or none)
-  unsigned long long ok_mine = (rc == CC_OK && !h_flag && !h_err && n_owned <= build_cap) ? 1 : 0;
+  const bool fits = kind != CC_HT_LP || 2 * (size_t) n_owned <= slots;
+  unsigned long long ok_mine = (rc == CC_OK && !h_flag && !h_err && n_owned <= build_cap && fits) ? 1 : 0;
   std::vector<unsigned long long> ok_all(P, 0);
   if (comm->allgather(comm->user, &ok_mine, ok_all.data(), sizeof(ok_mine)) != 0) rc = CC_ERR_INVALID;
   bool all_ok = rc == CC_OK;
@@ -381,23 +445,22 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     cudaFree(d_build);
     cudaFree(d_cursor);
     if (rc == CC_OK) {
-      set_error("cc_pjoin_create: the build-side exchange failed on some rank (region overrun %d, wait timeout %d, %llu rows owned of %zu)", h_flag,
-                h_err, n_owned, build_cap);
+      set_error("cc_pjoin_create: the build-side exchange failed on some rank (here: region overrun %d, wait timeout %d, %llu rows owned, room for %zu, "
+                "table of %zu slots) -- heavily skewed build keys",
+                h_flag, h_err, n_owned, build_cap, slots);
       rc = CC_ERR_UNSUPPORTED;
     }
     return fail(rc);
   }
   cudaMemsetAsync(j->d_flag, 0, sizeof(int), st);
-  // the reference's sizing rule on the GLOBAL key count, divided by the ranks (see cc_ht_build_sized)
-  size_t slots = 1;
-  const size_t per_key = kind == CC_HT_LP ? 4 : 2;
-  while (slots < per_key * (size_t) n_total) slots <<= 1;
-  slots = std::max<size_t>(1, slots / P);
-  while (kind == CC_HT_LP && slots < 2 * (size_t) n_owned) slots <<= 1;
-  rc = cc_ht_build_sized(&j->table, kind, d_build, (size_t) n_owned, P > 1 ? slots : 0, CC_BUILD_ORDERED, s);
+  rc = cc_ht_build_sized(&j->table, kind, d_build, (size_t) n_owned, slots, CC_BUILD_ORDERED, s);
   cudaFree(d_build);
   cudaFree(d_cursor);
   if (rc != CC_OK) return fail(rc);
+  if (j->table->n_slots != slots) {
+    set_error("cc_pjoin_create: internal error: table of %zu slots, %zu expected", j->table->n_slots, slots);
+    return fail(CC_ERR_INVALID);
+  }
   *out = j;
   return CC_OK;
 }
@@ -407,35 +470,34 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
   CC_TRY(require_device());
   CC_REQUIRE(j && d_result, "NULL argument");
   CC_REQUIRE(n == 0 || d_keys, "d_keys is NULL");
-  CC_REQUIRE(n <= j->max_rows * (size_t) j->n_sub, "%zu probe rows exceed the %zu this join was sized for", n, j->max_rows * (size_t) j->n_sub);
+  CC_REQUIRE(n <= j->max_rows * (size_t) j->pieces, "%zu probe rows exceed the %zu this join was sized for", n, j->max_rows * (size_t) j->pieces);
   cudaStream_t st = as_stream(s);
+  const PjLayout &lay = j->lay;
+  const int P = j->world, B = j->pieces, S = j->slices;
   const size_t cap = (d_out_key || d_out_payload) ? out_capacity : 0;
-  PJ_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
-  // EVERY rank runs n_sub shuffles per call, whatever its own row count: the sub-batch boundaries only depend on n_sub
-  const int n_sub = j->n_sub;
-  const size_t per = (n + n_sub - 1) / n_sub;
-  auto piece = [&](int b, const int64_t **p, size_t *cnt) {
-    const size_t off = std::min(n, (size_t) b * per);
-    *cnt = std::min(per, n - off);
-    *p = *cnt ? d_keys + off : nullptr;
-  };
-  std::vector<unsigned long long> ks(n_sub);
-  const int64_t *p = nullptr;
-  size_t cnt = 0;
-  piece(0, &p, &cnt);
-  CC_TRY(shuffle_start(j, p, cnt, st, &ks[0]));
-  for (int b = 0; b < n_sub; ++b) {
-    if (b + 1 < n_sub) {
-      piece(b + 1, &p, &cnt);
-      CC_TRY(shuffle_start(j, p, cnt, st, &ks[b + 1]));  // its copies run underneath the probe of sub-batch b
-    }
-    const int64_t *col = nullptr;
-    SegIn seg;
-    CC_TRY(shuffle_finish(j, ks[b], st, &col, &seg));
-    CC_TRY(probe_segmented_device(j->table, col, seg, d_out_key, d_out_payload, cap, d_result, st, /*accumulate=*/true));
-    CC_TRY(shuffle_consumed(j, ks[b], st));
+  const int arena = (int) (j->uses % kPjArenas);
+  const unsigned long long epoch = j->uses / kPjArenas + 1;
+  ++j->uses;
+  // EVERY rank sends B pieces per call, whatever its own row count: the piece boundaries only depend on B
+  const size_t per = (n + B - 1) / B;
+  for (int b = 0; b < B; ++b) {
+    const size_t off = std::min(n, (size_t) b * per), cnt = std::min(per, n - off);
+    CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, S, j->log2s, arena, b, epoch, b == 0, st));
   }
+  pj_wait_kernel<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, 0, 0), B * P, epoch, j->d_err);
+  CC_CHECK_LAUNCH();
+  // the arena [piece][sender][slice] is walked slice by slice: all pieces and senders of one table slice, then the next slice
+  SegIn seg;
+  seg.counts = j->counts(arena);
+  seg.cap = lay.cap;
+  seg.segments = B * P * S;
+  seg.inner = B * P;
+  seg.outer_stride = lay.Sa;
+  seg.presliced = S > 1;
+  CC_TRY(probe_segmented_device(j->table, j->arena(j->rank, arena), seg, d_out_key, d_out_payload, cap, d_result, st, /*accumulate=*/false));
   pj_close_kernel<<<1, 32, 0, st>>>(d_result, cap, j->d_flag, j->d_err);
+  CC_CHECK_LAUNCH();
+  pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), lay, j->rank, arena, epoch);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

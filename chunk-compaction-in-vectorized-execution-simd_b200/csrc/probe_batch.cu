@@ -66,6 +66,7 @@ struct ProbeArgs {
   const unsigned long long *seg_cursors;
   unsigned long long seg_cap;
   int seg_parts;
+  int seg_inner = 0, seg_outer_stride = 0;  // walk order != memory order (SegIn::region, partition.cuh); 0 = identity
   const int *gate;  // optional device-side switch: run only if (*gate != 0) == gate_want
   int gate_want;
   // payload columns (PAY kernels only): pay[c][i] belongs to the table entry at index i (LP slot / chain position)
@@ -123,6 +124,11 @@ __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v, const CachePo
     asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// memory region of walk segment p (SegIn::region)
+__device__ __forceinline__ uint32_t seg_region(const ProbeArgs &a, uint32_t p) {
+  return a.seg_inner ? (p % (uint32_t) a.seg_inner) * (uint32_t) a.seg_outer_stride + p / (uint32_t) a.seg_inner : p;
+}
+
 struct ProbeShared {
   uint32_t cnt[32];
   unsigned long long base;
@@ -150,9 +156,10 @@ __device__ __forceinline__ bool tile_lookup(const ProbeArgs &a, const ProbeShare
   const unsigned long long first = (unsigned long long) local * kPbTile;
   // region fill count through the read-only L1 path (the same few regions are asked for again and again); a shared-memory
   // copy would grow the carve-out, which costs this chip gather throughput
-  unsigned long long cnt = __ldg(a.seg_cursors + p);
+  const uint32_t reg = seg_region(a, p);
+  unsigned long long cnt = __ldg(a.seg_cursors + reg);
   if (cnt > a.seg_cap) cnt = a.seg_cap;
-  off = (unsigned long long) p * a.seg_cap + first;
+  off = (unsigned long long) reg * a.seg_cap + first;
   rows = cnt > first ? (uint32_t) (cnt - first < (unsigned long long) kPbTile ? cnt - first : (unsigned long long) kPbTile) : 0u;
   return true;
 }
@@ -557,7 +564,7 @@ __device__ __forceinline__ void lean_tile(const ProbeArgs &a, LeanShared &sh, un
       lo = hi;
       hi = __ldg(a.seg_prefix + p + 1);
     } while ((uint32_t) g >= hi);
-    unsigned long long c = __ldg(a.seg_cursors + p);
+    unsigned long long c = __ldg(a.seg_cursors + seg_region(a, p));
     sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
     sh.seg_p = p;
     sh.seg_lo = lo;
@@ -565,7 +572,7 @@ __device__ __forceinline__ void lean_tile(const ProbeArgs &a, LeanShared &sh, un
   }
   const unsigned long long first = (unsigned long long) ((uint32_t) g - lo) * kPbTile;
   const unsigned long long left = sh.seg_cnt - first;
-  off = (unsigned long long) p * a.seg_cap + first;
+  off = (unsigned long long) seg_region(a, p) * a.seg_cap + first;
   rows = left < (unsigned long long) kPbTile ? (uint32_t) left : (uint32_t) kPbTile;
 }
 
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(kPbThreads, CCB_LEAN_MIN_BLOCKS) probe_unique_
   uint64_t ksum = 0;
   if (threadIdx.x == 0) {
     if (a.seg_parts) {
-      unsigned long long c = a.seg_cursors[0];
+      unsigned long long c = a.seg_cursors[seg_region(a, 0)];
       sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
       sh.seg_p = 0;
       sh.seg_lo = 0;
@@ -859,7 +866,7 @@ __device__ __forceinline__ void lean_tile_t(const ProbeArgs &a, SH &sh, unsigned
       lo = hi;
       hi = __ldg(a.seg_prefix + p + 1);
     } while ((uint32_t) g >= hi);
-    unsigned long long c = __ldg(a.seg_cursors + p);
+    unsigned long long c = __ldg(a.seg_cursors + seg_region(a, p));
     sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
     sh.seg_p = p;
     sh.seg_lo = lo;
@@ -867,7 +874,7 @@ __device__ __forceinline__ void lean_tile_t(const ProbeArgs &a, SH &sh, unsigned
   }
   const unsigned long long first = (unsigned long long) ((uint32_t) g - lo) * kPbTile;
   const unsigned long long left = sh.seg_cnt - first;
-  off = (unsigned long long) p * a.seg_cap + first;
+  off = (unsigned long long) seg_region(a, p) * a.seg_cap + first;
   rows = left < (unsigned long long) kPbTile ? (uint32_t) left : (uint32_t) kPbTile;
 }
 
@@ -882,7 +889,7 @@ __global__ void __launch_bounds__(kPbThreads, CCB_LEAN_MIN_BLOCKS) probe_unique_
   uint64_t ksum = 0;
   if (threadIdx.x == 0) {
     if (a.seg_parts) {
-      unsigned long long c = a.seg_cursors[0];
+      unsigned long long c = a.seg_cursors[seg_region(a, 0)];
       sh.seg_cnt = c < a.seg_cap ? c : a.seg_cap;
       sh.seg_p = 0;
       sh.seg_lo = 0;
@@ -1121,11 +1128,14 @@ static int launch_probe_lean_lp_out(const ProbeArgs &a, cudaStream_t st) {
   return CC_OK;
 }
 
-// A/B switch for measurements: CCB_LEAN_INLINE_TAIL=1 keeps the round-1 kernel (tail walk inside the iteration) for LP tables
+// A/B switch for measurements: CCB_LEAN_DEFERRED_TAIL=1 selects probe_unique_lp_kernel (tail walk deferred through the per-warp
+// ring).  MEASURED SLOWER than the inline tail walk of probe_unique_kernel on the C4 step (18.45 vs 17.75 ms,
+// profiles/r2_probe_deferred_tail_ab.txt): removing the dependent round trips does not pay because the kernel is bound by L1
+// wavefront throughput, not by that latency -- so the inline walk stays the default and this kernel stays as the evidence.
 static bool deferred_tail_enabled() {
   static const bool on = [] {
-    const char *e = getenv("CCB_LEAN_INLINE_TAIL");
-    return !(e && e[0] == '1');
+    const char *e = getenv("CCB_LEAN_DEFERRED_TAIL");
+    return e && e[0] == '1';
   }();
   return on;
 }
@@ -1265,7 +1275,7 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
   a.gate_want = 0;
   if (!accumulate) CC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
   if (n) {
-    const bool part = want_partitioned(ht, n, d_out_rowid, pay.n);
+    const bool part = !seg.presliced && want_partitioned(ht, n, d_out_rowid, pay.n);
     size_t table_bytes = probed_table_bytes(ht, pay.n);
     int log2_slots = log2_floor(ht->n_slots);
     int log2p = log2_floor((table_bytes + g_slice_bytes - 1) / g_slice_bytes);
@@ -1344,13 +1354,16 @@ int probe_batch_device(const cc_ht *ht, const int64_t *d_keys, size_t n, int64_t
       profile_mark(2, st);
       if (seg.cap) {  // probe the segmented column in place
         uint32_t *prefix = reinterpret_cast<uint32_t *>(ctl + 8);
-        rc = seg_prefix_device(seg.counts, seg.segments, seg.cap, kPbTile, prefix, st);
+        rc = seg_prefix_device(seg.counts, seg.segments, seg.cap, kPbTile, prefix, st, seg);
         a.seg_prefix = prefix;
         a.seg_cursors = seg.counts;
         a.seg_cap = seg.cap;
         a.seg_parts = seg.segments;
+        a.seg_inner = seg.inner;
+        a.seg_outer_stride = seg.outer_stride;
       }
-      if (rc == CC_OK) rc = dispatch_probe(g_mode_direct, ht, a, st);
+      // regions that already are table slices are probed with the cache hints of the partitioned strategy
+      if (rc == CC_OK) rc = dispatch_probe(seg.presliced ? g_mode_partitioned : g_mode_direct, ht, a, st);
       profile_mark(3, st);
       g_ev_valid = g_profile ? 1 : 0;
     }

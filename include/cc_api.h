@@ -342,11 +342,29 @@ int cc_chain_execute(const cc_ht *const *h_tables, size_t n_joins, const int64_t
                      const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
                      cc_chain_result *d_result, cc_stream_t stream);
 
+/* Chunk-density telemetry (the ZebraProfiler of profiler.h:168-260 keeps a histogram keyed by chunk size; compiled off in the
+ * reference, `kEnableProfiling = 0`, :170): per join level, how full the chunks were that the level's Probe received and that
+ * its Next rounds ran with, in CC_DENSITY_BINS equal bins of the pipeline instance's chunk width (bin 7 = 87.5 .. 100 %).
+ * This is what a compaction threshold moves: bin 7 holds nearly everything under full compaction, the low bins fill up
+ * without it.  cc_chain_execute_ex ADDS to *d_telemetry (clear it first); NULL = off.  cc_chain_telemetry_csv writes a HOST
+ * copy as CSV (histogram, level, density_from, density_to, chunks).                                                         */
+#define CC_DENSITY_BINS 8
+typedef struct {
+  uint64_t probe_rows_hist[CC_MAX_JOINS][CC_DENSITY_BINS];  /* chunks handed to a level's Probe, by fill              */
+  uint64_t round_lanes_hist[CC_MAX_JOINS][CC_DENSITY_BINS]; /* Next rounds of a level, by live lanes                  */
+} cc_chain_telemetry;
+int cc_chain_execute_ex(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
+                        const uint32_t *thresholds, int64_t *const *h_out_cols, size_t out_capacity,
+                        cc_chain_result *d_result, cc_chain_telemetry *d_telemetry, cc_stream_t stream);
+int cc_chain_telemetry_csv(const cc_chain_telemetry *h_telemetry, size_t n_joins, const char *path);
+
 /* Dynamic ("negative feedback") compaction (main.cpp:137-167 under flag_dynamic_compact): the LHS table
  * runs through cc_chain_execute in batches of batch_rows; before each batch bandit first_bandit_id + L
  * of `tuner` selects the threshold of join L (SelectArm), afterwards every bandit is rewarded with
- * 2 / seconds / 1e3 (main.cpp:166), seconds = device time of the batch.  Synchronous; the accumulated
- * result is written to the HOST struct *h_result.                                                   */
+ * 2 / seconds / 1e3 (main.cpp:166), seconds = device time of the batch.  The batches are pipelined three
+ * deep (a bandit selects with the feedback of all batches but the last two; one deep when rows are
+ * materialised); the call returns when all of them are done and writes the accumulated result to the
+ * HOST struct *h_result.                                                                             */
 int cc_chain_execute_tuned(const cc_ht *const *h_tables, size_t n_joins, const int64_t *const *h_lhs_cols, size_t n_rows,
                            size_t batch_rows, cc_tuner *tuner, size_t first_bandit_id, int64_t *const *h_out_cols,
                            size_t out_capacity, cc_chain_result *h_result, cc_stream_t stream);

@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on a B200): every CUDA path of the product, called
 through the C ABI, against the CPU oracle and the committed golden fixtures.
 Integer work => bit-exact comparisons everywhere."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -326,6 +328,23 @@ def test_probe_batch_clustered_keys(ccb, strategy):
         assert np.array_equal(G.sort_rows(got), G.sort_rows(want["tuples"]))
         r2 = gtab.probe_batch(dev(probe), materialize=False)
         assert (r2["n_matches"], r2["key_sum"]) == (m, r["key_sum"])
+
+
+def test_deferred_tail_kernel_parity(ccb):
+    """probe_unique_lp_kernel (the deferred tail walk, CCB_LEAN_DEFERRED_TAIL=1 -- measured slower and therefore not the default,
+    profiles/r2_probe_deferred_tail_ab.txt) must stay correct: the switch is read once per process, so the LP probe tests
+    that stress it (clustered keys, extreme keys, DRAM-resident properties, all strategies) run again in a child process."""
+    import subprocess
+    import sys
+
+    if os.environ.get("CCB_LEAN_DEFERRED_TAIL") == "1":
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, CCB_LEAN_DEFERRED_TAIL="1")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "clustered_keys or negative_and_extreme or probe_batch_large_properties or (probe_batch_matches_oracle and 1024)"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert " passed" in p.stdout and "failed" not in p.stdout
 
 
 def test_probe_batch_microbench_known_answer(ccb):
