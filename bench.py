@@ -329,7 +329,7 @@ def main() -> int:
     if args.log2_probe is None:
         args.log2_probe = 31 if args.gpus == 1 else 30
     if args.sub_batches is None:
-        args.sub_batches = 4 if (args.gpus > 1 and args.exchange in ("ce", "cabi")) else 1
+        args.sub_batches = (8 if args.exchange == "cabi" else 4) if (args.gpus > 1 and args.exchange in ("ce", "cabi")) else 1
     if args.impl == "reference":
         return run_reference_arm(args)
 

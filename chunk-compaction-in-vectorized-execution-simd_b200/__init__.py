@@ -612,8 +612,11 @@ class CompactTuner:
 
 # ---- fused join chain ---------------------------------------------------------------------
 def chain_execute(tables: Sequence[_TableBase], lhs_cols: Sequence[torch.Tensor], thresholds: Optional[Sequence[int]] = None,
-                  materialize: bool = False, capacity: int = 0, result: Optional[torch.Tensor] = None, sync: bool = True) -> dict:
-    """ExecutePipeline + FlushPipelineCache (main.cpp:119-191) for a whole LHS table in one kernel."""
+                  materialize: bool = False, capacity: int = 0, result: Optional[torch.Tensor] = None, sync: bool = True,
+                  telemetry: Optional[torch.Tensor] = None) -> dict:
+    """ExecutePipeline + FlushPipelineCache (main.cpp:119-191) for a whole LHS table in one kernel.
+    telemetry: an int64 device tensor from new_chain_telemetry() -- the chunk-density histograms of this call are ADDED to it
+    (cc_chain_execute_ex; parse with parse_chain_telemetry)."""
     _ensure()
     J = len(tables)
     assert len(lhs_cols) == J
@@ -631,7 +634,7 @@ def chain_execute(tables: Sequence[_TableBase], lhs_cols: Sequence[torch.Tensor]
         op = (C.c_void_p * (3 * J))(*[o.data_ptr() for o in outs])
     if result is None:
         result = torch.zeros(C.sizeof(ChainResult) // 8, dtype=torch.int64, device="cuda")
-    L.check(lib().cc_chain_execute(tp, J, cp, n_rows, thr, op, capacity, _ptr(result), _stream()))
+    L.check(lib().cc_chain_execute_ex(tp, J, cp, n_rows, thr, op, capacity, _ptr(result), _ptr(telemetry), _stream()))
     out = {"result_tensor": result, "out_cols": outs}
     if sync:
         out.update(parse_chain_result(result, J))
@@ -655,6 +658,24 @@ def chain_execute_tuned(tables: Sequence[_TableBase], lhs_cols: Sequence[torch.T
     out = _chain_result_dict(r, J)
     out["out_cols"] = outs
     return out
+
+
+def new_chain_telemetry() -> torch.Tensor:
+    """zeroed cc_chain_telemetry on the device (chunk-density histograms, the ZebraProfiler analogue of profiler.h:168-260)"""
+    _ensure()
+    return torch.zeros(C.sizeof(L.ChainTelemetry) // 8, dtype=torch.int64, device="cuda")
+
+
+def parse_chain_telemetry(telemetry: torch.Tensor, J: int) -> dict:
+    t = L.ChainTelemetry.from_buffer_copy(telemetry.cpu().numpy().tobytes())
+    return {"probe_rows_hist": [[int(t.probe_rows_hist[l][q]) for q in range(L.CC_DENSITY_BINS)] for l in range(J)],
+            "round_lanes_hist": [[int(t.round_lanes_hist[l][q]) for q in range(L.CC_DENSITY_BINS)] for l in range(J)], "_struct": t}
+
+
+def chain_telemetry_csv(telemetry: torch.Tensor, J: int, path: str) -> None:
+    """cc_chain_telemetry_csv: histogram, level, density_from, density_to, chunks"""
+    t = L.ChainTelemetry.from_buffer_copy(telemetry.cpu().numpy().tobytes())
+    L.check(lib().cc_chain_telemetry_csv(C.byref(t), J, path.encode()))
 
 
 def parse_chain_result(result: torch.Tensor, J: int) -> dict:

@@ -24,7 +24,10 @@
 // only job is the control plane at create / destroy time (exchange of the IPC handles and sizes through the caller's cc_comm
 // callbacks: MPI, torch.distributed, or the fork + shared-memory communicator of host/simd_compaction.hpp).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -478,14 +481,30 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
   const int arena = (int) (j->uses % kPjArenas);
   const unsigned long long epoch = j->uses / kPjArenas + 1;
   ++j->uses;
+  // evidence switch CCB_PJ_TRACE=1: CUDA-event timeline of the call on `st` (synchronises; printed by every rank)
+  static const bool trace = [] {
+    const char *e = getenv("CCB_PJ_TRACE");
+    return e && e[0] == '1';
+  }();
+  std::vector<cudaEvent_t> marks;
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    marks.push_back(ev);
+  };
+  mark();
   // EVERY rank sends B pieces per call, whatever its own row count: the piece boundaries only depend on B
   const size_t per = (n + B - 1) / B;
   for (int b = 0; b < B; ++b) {
     const size_t off = std::min(n, (size_t) b * per), cnt = std::min(per, n - off);
     CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, S, j->log2s, arena, b, epoch, b == 0, st));
+    mark();
   }
   pj_wait_kernel<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, 0, 0), B * P, epoch, j->d_err);
   CC_CHECK_LAUNCH();
+  mark();
   // the arena [piece][sender][slice] is walked slice by slice: all pieces and senders of one table slice, then the next slice
   SegIn seg;
   seg.counts = j->counts(arena);
@@ -499,6 +518,25 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
   CC_CHECK_LAUNCH();
   pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), lay, j->rank, arena, epoch);
   CC_CHECK_LAUNCH();
+  if (trace) {
+    mark();
+    cudaStreamSynchronize(st);
+    std::string line = "pjoin timeline rank " + std::to_string(j->rank) + " (ms since begin, " + std::to_string(B) + " pieces, " + std::to_string(S) +
+                       " slices):";
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[0], marks[i]);
+      char buf[64];
+      const char *name = i <= (size_t) B ? "F" : (i == (size_t) B + 1 ? "WAIT" : "PROBE");
+      if (i <= (size_t) B)
+        snprintf(buf, sizeof(buf), " %s%zu=%.2f", name, i - 1, ms);
+      else
+        snprintf(buf, sizeof(buf), " %s=%.2f", name, ms);
+      line += buf;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (auto ev : marks) cudaEventDestroy(ev);
+  }
   return CC_OK;
 }
 

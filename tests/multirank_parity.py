@@ -2,7 +2,7 @@
 """Multi-rank GPU parity gate for the hash-partitioned join ("1/2/4/8-GPU partitioned == 1-GPU == CPU").
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 --master-port 29611 \
-        tests/multirank_parity.py [--log profiles/r2_multirank_parity_pP.txt]
+        tests/multirank_parity.py [--report profiles/r2_multirank_parity_pP.txt]
 
 One process per GPU (NCCL).  For BOTH table kinds (linear probing: linear_probing_ht.cpp:62-115 -- lanes walk past a match,
 duplicates sit in separate slots; separate chaining: chaining_ht.cpp:60-136), chunk_factor in {1, 4, 8}, hit in {1, 2}, every
@@ -64,7 +64,7 @@ def all_ok(flag: bool, dev) -> bool:
 
 def main() -> int:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--log", default=None)
+    ap.add_argument("--report", default=None, help="write the PASS / FAIL lines to this file (rank 0)")
     ap.add_argument("--log2-build", type=int, default=18, help="build keys of the whole join")
     ap.add_argument("--log2-probe", type=int, default=20, help="probe keys of the whole join")
     ap.add_argument("--quick", action="store_true", help="cf in {1, 4} and hit 2 only")
@@ -269,9 +269,9 @@ def main() -> int:
         del join
 
     say(f"# {'ALL GREEN' if not failures else 'FAILURES: ' + '; '.join(failures)}  ({time.time() - t_start:.1f} s)")
-    if rank == 0 and args.log:
-        os.makedirs(os.path.dirname(os.path.abspath(args.log)), exist_ok=True)
-        with open(args.log, "w") as f:
+    if rank == 0 and args.report:
+        os.makedirs(os.path.dirname(os.path.abspath(args.report)), exist_ok=True)
+        with open(args.report, "w") as f:
             f.write("\n".join(lines) + "\n")
     dist.barrier()
     dist.destroy_process_group()
