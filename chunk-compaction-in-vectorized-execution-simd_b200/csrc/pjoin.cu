@@ -233,13 +233,20 @@ int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, i
   }
   PJ_CUDA(cudaEventRecord(j->gate, c0));
   for (int s = 1; s < kPjCopyStreams; ++s) PJ_CUDA(cudaStreamWaitEvent(j->cs[s], j->gate, 0));
-  const size_t bytes = (size_t) S * lay.cap * 8;
+  // one stream drives one copy engine at a time and a single engine does not fill an NVLink 5 port (measured at P = 2 with one
+  // copy per piece: 450 GB/s): with fewer destinations than copy streams every block is cut into chunks dealt over the streams
+  const size_t rows = (size_t) S * lay.cap;
+  const int dests = (self && P > 1) ? P - 1 : P;
+  const int chunks = dests >= kPjCopyStreams ? 1 : (kPjCopyStreams + dests - 1) / dests;
+  const size_t chunk_rows = ((rows + chunks - 1) / chunks + 511) / 512 * 512;
   int n_copy = 0;
   for (int i = 0; i < P; ++i) {
     const int o = (j->rank + i) % P;  // stagger the destinations so that the ranks do not all hit the same peer at once
     if (o == j->rank && self && P > 1) continue;  // written in place by the scatter kernel
-    PJ_CUDA(cudaMemcpyAsync(j->arena(o, arena) + lay.region_index(piece, j->rank, 0) * lay.cap, j->send[slot] + (size_t) o * S * lay.cap, bytes,
-                            cudaMemcpyDeviceToDevice, j->cs[n_copy++ % kPjCopyStreams]));
+    int64_t *dst = j->arena(o, arena) + lay.region_index(piece, j->rank, 0) * lay.cap;
+    const int64_t *src = j->send[slot] + (size_t) o * rows;
+    for (size_t at = 0; at < rows; at += chunk_rows)
+      PJ_CUDA(cudaMemcpyAsync(dst + at, src + at, std::min(chunk_rows, rows - at) * 8, cudaMemcpyDeviceToDevice, j->cs[n_copy++ % kPjCopyStreams]));
   }
   for (int s = 1; s < kPjCopyStreams; ++s) {
     PJ_CUDA(cudaEventRecord(j->joined[s], j->cs[s]));
@@ -330,9 +337,19 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   j->table_slots = slots;
   // table slices: L2-sized, a power of two, at most kMaxParts / P (the scatter kernel ranks P * S partitions per tile)
   const size_t table_bytes = kind == CC_HT_LP ? slots * 8 : slots * 8 + (size_t) (n_total / P) * 8;
+  // test switch CCB_PJ_SLICE_BYTES=<bytes>: slice size (and half the smallest table that is sliced), so that small tables take
+  // the fused owner x slice path too
+  size_t slice_bytes = kPjSliceBytes, min_table = kPjSliceMinTable;
+  if (const char *e = getenv("CCB_PJ_SLICE_BYTES")) {
+    const long long v = atoll(e);
+    if (v >= 1024) {
+      slice_bytes = (size_t) v;
+      min_table = 2 * slice_bytes;
+    }
+  }
   int S = 1, log2s = 0;
-  if (table_bytes >= kPjSliceMinTable && slots <= (1ull << 32)) {
-    while ((size_t) S * kPjSliceBytes < table_bytes && S * 2 * P <= kMaxParts && (size_t) S * 2 <= slots) {
+  if (table_bytes >= min_table && slots <= (1ull << 32)) {
+    while ((size_t) S * slice_bytes < table_bytes && S * 2 * P <= kMaxParts && (size_t) S * 2 <= slots) {
       S *= 2;
       ++log2s;
     }
@@ -502,18 +519,29 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
     CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, S, j->log2s, arena, b, epoch, b == 0, st));
     mark();
   }
-  pj_wait_kernel<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, 0, 0), B * P, epoch, j->d_err);
-  CC_CHECK_LAUNCH();
-  mark();
-  // the arena [piece][sender][slice] is walked slice by slice: all pieces and senders of one table slice, then the next slice
-  SegIn seg;
-  seg.counts = j->counts(arena);
-  seg.cap = lay.cap;
-  seg.segments = B * P * S;
-  seg.inner = B * P;
-  seg.outer_stride = lay.Sa;
-  seg.presliced = S > 1;
-  CC_TRY(probe_segmented_device(j->table, j->arena(j->rank, arena), seg, d_out_key, d_out_payload, cap, d_result, st, /*accumulate=*/false));
+  // The pieces are probed in (at most) two groups: the first half while the second half is still on its way -- the copy chain of
+  // the last pieces hides under the first probe at the price of streaming the table twice (+ table_bytes / HBM rate per step).
+  // Within a group the arena [piece][sender][slice] is walked slice by slice: all pieces and senders of one table slice, then the
+  // next slice.
+  PJ_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
+  const int groups = (B >= 4 && P > 1) ? 2 : 1;
+  for (int g = 0; g < groups; ++g) {
+    const int b0 = g * B / groups, b1 = (g + 1) * B / groups;
+    pj_wait_kernel<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, b0, 0), (b1 - b0) * P, epoch,
+                                     j->d_err);
+    CC_CHECK_LAUNCH();
+    mark();
+    SegIn seg;
+    seg.counts = j->counts(arena) + lay.region_index(b0, 0, 0);
+    seg.cap = lay.cap;
+    seg.segments = (b1 - b0) * P * S;
+    seg.inner = (b1 - b0) * P;
+    seg.outer_stride = lay.Sa;
+    seg.presliced = S > 1;
+    CC_TRY(probe_segmented_device(j->table, j->arena(j->rank, arena) + lay.region_index(b0, 0, 0) * lay.cap, seg, d_out_key, d_out_payload, cap, d_result, st,
+                                  /*accumulate=*/true));
+    mark();
+  }
   pj_close_kernel<<<1, 32, 0, st>>>(d_result, cap, j->d_flag, j->d_err);
   CC_CHECK_LAUNCH();
   pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), lay, j->rank, arena, epoch);
@@ -527,11 +555,12 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
       float ms = 0;
       cudaEventElapsedTime(&ms, marks[0], marks[i]);
       char buf[64];
-      const char *name = i <= (size_t) B ? "F" : (i == (size_t) B + 1 ? "WAIT" : "PROBE");
       if (i <= (size_t) B)
-        snprintf(buf, sizeof(buf), " %s%zu=%.2f", name, i - 1, ms);
+        snprintf(buf, sizeof(buf), " F%zu=%.2f", i - 1, ms);
+      else if (i + 1 == marks.size())
+        snprintf(buf, sizeof(buf), " END=%.2f", ms);
       else
-        snprintf(buf, sizeof(buf), " %s=%.2f", name, ms);
+        snprintf(buf, sizeof(buf), " %s%zu=%.2f", ((i - B) & 1) ? "WAIT" : "PROBE", (i - B - 1) / 2, ms);
       line += buf;
     }
     fprintf(stderr, "%s\n", line.c_str());

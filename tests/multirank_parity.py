@@ -82,6 +82,7 @@ def main() -> int:
 
     if args.partitioned_probe:
         pkg.set_probe_strategy(2, 1 << 20)
+        os.environ["CCB_PJ_SLICE_BYTES"] = str(64 << 10)  # the C-ABI join then groups by (owner, 64 KiB table slice) on the sender
 
     sys.stdout.flush()
     dist.init_process_group("nccl", device_id=dev)

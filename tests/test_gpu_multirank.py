@@ -46,8 +46,13 @@ def test_cpp_pjoin_driver_matches_oracle(ccb, tmp_path, world, table, cf, hit):
     assert os.path.exists(PJOIN), "build it with make -C <pkg>/csrc driver"
     lb, lp = 16, 19
     prefix = str(tmp_path / "rows")
+    # tables of 2^16 keys live in L2; CCB_PJ_SLICE_BYTES makes the join slice them anyway (fused owner x slice partition on the sender,
+    # arenas probed slice by slice in two groups of pieces), once per table kind
+    env = dict(os.environ)
+    if cf != 8:
+        env["CCB_PJ_SLICE_BYTES"] = str(32 << 10)
     out = subprocess.run([PJOIN, "--gpus", str(world), "--log2-build", str(lb), "--log2-probe", str(lp), "--table", table, "--chunk-factor", str(cf),
-                          "--hit", str(hit), "--steps", "2", "--sub-batches", "5", "--dump", prefix], capture_output=True, text=True, timeout=600)
+                          "--hit", str(hit), "--steps", "2", "--sub-batches", "5", "--dump", prefix], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["checks_ok"] and r["owner_property"] and r["overflow"] == 0 and r["n_matches"] == r["expected_matches"]
