@@ -14,12 +14,17 @@
 //   * copy engines: the regions of owner o travel as ONE cudaMemcpyAsync into slot [piece][this rank] of o's receive arena
 //     (CUDA-IPC mapping of peer memory over NVLink 5 / NVSwitch), on several copy streams, without occupying an SM; the rows a
 //     rank keeps are written straight into its own arena by the scatter kernel;
-//   * pj_signal_kernel: stores the regions' row counts and an epoch flag into the owner's control block over NVLink, behind the
-//     copies in stream order ("piece b of this step from sender s has landed");
-//   * pj_wait_kernel: the owner's stream spins (bounded) on its own flags until every piece of every sender has arrived, then
-//     ONE probe walks the arena slice by slice (all pieces and senders of slice 0, then slice 1, ...: the table is streamed
-//     from HBM once per step); pj_consumed_kernel then tells every sender that the arena may be refilled (two arenas alternate
-//     between steps, so the copies of step t + 1 land while step t is still being probed).
+//   * signal: behind the copies in stream order, the regions' row counts (a small copy) and an epoch flag are written into the
+//     owner's control block over NVLink ("piece b of this step from sender s has landed");
+//   * wait: the owner's stream waits for the flags of the pieces it is about to probe, then a probe walks their part of the
+//     arena slice by slice (all pieces and senders of slice 0, then slice 1, ...); a `consumed` flag then tells every sender
+//     that the arena may be refilled (two arenas alternate between steps, so the copies of step t + 1 land while step t is
+//     still being probed).
+//   Signals and waits are STREAM MEMORY OPERATIONS (cuStreamWriteValue64 / cuStreamWaitValue64, resolved through
+//   cudaGetDriverEntryPoint): they need no SM.  Small kernels were measured first and starve: the scatter and probe kernels
+//   fill every SM's register file, so a one-CTA signal kernel on another stream only runs at the next kernel boundary -- and the
+//   copies queued behind it wait with it (profiles/r2_pjoin_timeline_n2.txt).  The kernels remain as the fallback for drivers
+//   without stream memory operations on peer memory (bounded spins, error bit instead of a hang).
 // The host never learns a count and never blocks: a probe call enqueues  F(0) F(1) .. F(B-1) W PROBE C  and returns.  The host's
 // only job is the control plane at create / destroy time (exchange of the IPC handles and sizes through the caller's cc_comm
 // callbacks: MPI, torch.distributed, or the fork + shared-memory communicator of host/simd_compaction.hpp).
@@ -29,6 +34,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <cuda.h>  // types of the stream memory operations only: the entry points are resolved at run time, libcuda is not linked
 
 #include "common.cuh"
 #include "partition.cuh"
@@ -56,7 +63,7 @@ struct PjLayout {
     auto up = [](size_t x) { return (x + 4095) / 4096 * 4096; };
     ready_off = 0;
     consumed_off = up(ready_off + (size_t) kPjArenas * Ba * P * 8);
-    counts_off = up(consumed_off + (size_t) kPjArenas * kMaxPeers * 8);
+    counts_off = up(consumed_off + (size_t) (kPjArenas + 1) * kMaxPeers * 8);  // (+ one row of scratch words for the memory-operation self-test)
     data_off = up(counts_off + (size_t) kPjArenas * Ba * P * Sa * 8);
     total = data_off + (size_t) kPjArenas * arena_rows() * 8;
   }
@@ -71,6 +78,29 @@ static int log2_floor_pj(size_t x) {
   while ((x >> l) > 1) ++l;
   return l;
 }
+
+// stream memory operations of the driver API, resolved at run time (no link dependency on libcuda)
+struct PjMemOps {
+  typedef CUresult (*write_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+  typedef CUresult (*wait_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+  write_fn write = nullptr;
+  wait_fn wait = nullptr;
+  bool ok() const { return write && wait; }
+  static PjMemOps resolve() {
+    PjMemOps m;
+    const char *off = getenv("CCB_PJ_NO_MEMOPS");  // measurement / fallback switch: signal and wait with kernels
+    if (off && off[0] == '1') return m;
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &w, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWaitValue64", &q, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess) {
+      m.write = reinterpret_cast<write_fn>(w);
+      m.wait = reinterpret_cast<wait_fn>(q);
+    }
+    cudaGetLastError();
+    return m;
+  }
+};
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) {
   unsigned long long v;
@@ -175,6 +205,7 @@ struct cc_pjoin {
   unsigned long long uses = 0;                 // arena uses so far (arena = uses % kPjArenas, its epoch = uses / kPjArenas + 1)
   cc_ht *table = nullptr;
   size_t n_build_total = 0, table_slots = 0;
+  PjMemOps memops;                             // stream memory operations (empty: signal / wait with kernels)
 
   int64_t *arena(int r, int a) const { return reinterpret_cast<int64_t *>(peer_block[r] + lay.data_off) + (size_t) a * lay.arena_rows(); }
   unsigned long long *counts(int a) const {
@@ -198,6 +229,64 @@ PjPeers peers_of(const cc_pjoin *j) {
   PjPeers p;
   for (int r = 0; r < kMaxPeers; ++r) p.base[r] = r < j->world ? j->peer_block[r] : nullptr;
   return p;
+}
+
+unsigned long long *ready_flag(const cc_pjoin *j, int r, int arena, int piece, int sender) {
+  return reinterpret_cast<unsigned long long *>(j->peer_block[r] + j->lay.ready_off) + j->lay.flag_index(arena, piece, sender);
+}
+unsigned long long *consumed_flag(const cc_pjoin *j, int r, int arena, int receiver) {
+  return reinterpret_cast<unsigned long long *>(j->peer_block[r] + j->lay.consumed_off) + (size_t) arena * kMaxPeers + receiver;
+}
+
+#define PJ_DRV(expr)                                                                    \
+  do {                                                                                  \
+    CUresult r__ = (expr);                                                              \
+    if (r__ != CUDA_SUCCESS) {                                                          \
+      set_error("%s:%d: %s failed: CUresult %d", __FILE__, __LINE__, #expr, (int) r__); \
+      return CC_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+// `n` consecutive flags of THIS rank's control block must reach `epoch` before the work behind it on `st` runs
+int wait_flags(cc_pjoin *j, unsigned long long *flags, int n, unsigned long long epoch, cudaStream_t st) {
+  if (j->memops.ok()) {
+    for (int i = 0; i < n; ++i) PJ_DRV(j->memops.wait((CUstream) st, (CUdeviceptr) (flags + i), epoch, CU_STREAM_WAIT_VALUE_GEQ));
+    return CC_OK;
+  }
+  pj_wait_kernel<<<1, 256, 0, st>>>(flags, n, epoch, j->d_err);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// tells every owner (in stream order on `st`) that this rank's regions of (arena, piece) have landed, with their row counts
+int signal_piece(cc_pjoin *j, int arena, int piece, int S, const unsigned long long *d_counts, unsigned long long epoch, cudaStream_t st) {
+  const PjLayout &lay = j->lay;
+  if (!j->memops.ok()) {
+    pj_signal_kernel<<<j->world, 128, 0, st>>>(peers_of(j), lay, j->rank, arena, piece, S, d_counts, epoch);
+    CC_CHECK_LAUNCH();
+    return CC_OK;
+  }
+  for (int i = 0; i < j->world; ++i) {
+    const int o = (j->rank + i) % j->world;
+    unsigned long long *counts = reinterpret_cast<unsigned long long *>(j->peer_block[o] + lay.counts_off) +
+                                 ((size_t) arena * lay.Ba * lay.P * lay.Sa + lay.region_index(piece, j->rank, 0));
+    // raw fill counts (an overrun region was flagged by the scatter kernel; every reader clamps to the region capacity)
+    PJ_CUDA(cudaMemcpyAsync(counts, d_counts + (size_t) o * S, (size_t) S * 8, cudaMemcpyDeviceToDevice, st));
+    PJ_DRV(j->memops.write((CUstream) st, (CUdeviceptr) ready_flag(j, o, arena, piece, j->rank), epoch, CU_STREAM_WRITE_VALUE_DEFAULT));
+  }
+  return CC_OK;
+}
+
+// tells every sender that this rank has finished reading its arena `arena` (use `epoch`)
+int signal_consumed(cc_pjoin *j, int arena, unsigned long long epoch, cudaStream_t st) {
+  if (!j->memops.ok()) {
+    pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), j->lay, j->rank, arena, epoch);
+    CC_CHECK_LAUNCH();
+    return CC_OK;
+  }
+  for (int s = 0; s < j->world; ++s)
+    PJ_DRV(j->memops.write((CUstream) st, (CUdeviceptr) consumed_flag(j, s, arena, j->rank), epoch, CU_STREAM_WRITE_VALUE_DEFAULT));
+  return CC_OK;
 }
 
 // Sends one piece: the keys are grouped by (owner, slice) with `S` slices per owner (S == 1: by owner only) into a send slot,
@@ -227,10 +316,7 @@ int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, i
   PJ_CUDA(cudaEventRecord(j->parted[slot], st));
   cudaStream_t c0 = j->cs[0];
   PJ_CUDA(cudaStreamWaitEvent(c0, j->parted[slot], 0));
-  if (first_of_use && epoch > 1) {
-    pj_wait_kernel<<<1, 32, 0, c0>>>(reinterpret_cast<unsigned long long *>(j->block + lay.consumed_off) + (size_t) arena * kMaxPeers, P, epoch - 1, j->d_err);
-    CC_CHECK_LAUNCH();
-  }
+  if (first_of_use && epoch > 1) CC_TRY(wait_flags(j, consumed_flag(j, j->rank, arena, 0), P, epoch - 1, c0));
   PJ_CUDA(cudaEventRecord(j->gate, c0));
   for (int s = 1; s < kPjCopyStreams; ++s) PJ_CUDA(cudaStreamWaitEvent(j->cs[s], j->gate, 0));
   // one stream drives one copy engine at a time and a single engine does not fill an NVLink 5 port (measured at P = 2 with one
@@ -252,8 +338,7 @@ int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, i
     PJ_CUDA(cudaEventRecord(j->joined[s], j->cs[s]));
     PJ_CUDA(cudaStreamWaitEvent(c0, j->joined[s], 0));
   }
-  pj_signal_kernel<<<P, 128, 0, c0>>>(peers_of(j), lay, j->rank, arena, piece, S, counts, epoch);
-  CC_CHECK_LAUNCH();
+  CC_TRY(signal_piece(j, arena, piece, S, counts, epoch, c0));
   PJ_CUDA(cudaEventRecord(j->copied[slot], c0));
   return CC_OK;
 }
@@ -386,6 +471,7 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     return fail(e == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA);
   }
   j->peer_block[j->rank] = j->block;
+  j->memops = PjMemOps::resolve();
   if (P > 1) {
     cc_ipc_handle h_mine;
     rc = cc_ipc_export(j->block, &h_mine);
@@ -404,6 +490,19 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     }
   }
   if (comm->barrier(comm->user) != 0) return fail(CC_ERR_INVALID);  // every control block is zeroed and mapped before anyone signals
+  if (j->memops.ok()) {
+    // self-test: a stream memory operation on every peer's block (a scratch word per sender); a driver that refuses them on
+    // peer memory gets the kernel protocol instead (same flags, so ranks that decide differently still understand each other)
+    bool works = true;
+    for (int r = 0; r < P && works; ++r)
+      works = j->memops.write((CUstream) st, (CUdeviceptr) consumed_flag(j, r, kPjArenas, j->rank), 1, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS;
+    if (works) works = j->memops.wait((CUstream) st, (CUdeviceptr) consumed_flag(j, j->rank, kPjArenas, j->rank), 1, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
+    if (works) works = cudaStreamSynchronize(st) == cudaSuccess;
+    if (!works) {
+      cudaGetLastError();
+      j->memops = PjMemOps();
+    }
+  }
   // ---- build side: exchanged piece by piece by owner only (one region per owner), appended to a dense column
   const size_t piece_rows = std::max<size_t>(1, (size_t) ((lay.cap - 2 * (unsigned long long) kPartTile) * 32 / 33) * P);  // its owner shares fit a region
   const size_t pieces = (size_t) ((max_local + piece_rows - 1) / piece_rows);
@@ -428,17 +527,16 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
     ++j->uses;
     rc = send_piece(j, cnt ? d_build_keys + off : nullptr, cnt, /*S=*/1, 0, arena, /*piece=*/0, epoch, true, st);
     if (rc != CC_OK) break;
-    pj_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, 0, 0), P, epoch, j->d_err);
-    note_launch();
+    rc = wait_flags(j, ready_flag(j, j->rank, arena, 0, 0), P, epoch, st);
+    if (rc != CC_OK) break;
     // one region per sender: region_index(0, sender, 0) = sender * Sa
     pj_compact_kernel<<<sm_count() * 4, 256, 0, st>>>(j->arena(j->rank, arena), j->counts(arena), lay.cap, P, (size_t) lay.Sa * lay.cap, (size_t) lay.Sa,
                                                     d_build, build_cap, d_cursor);
     note_launch();
     pj_advance_kernel<<<1, 32, 0, st>>>(j->counts(arena), lay.cap, P, (size_t) lay.Sa, d_cursor);
     note_launch();
-    pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), lay, j->rank, arena, epoch);
-    note_launch();
     if (cudaGetLastError() != cudaSuccess) rc = CC_ERR_CUDA;
+    if (rc == CC_OK) rc = signal_consumed(j, arena, epoch, st);
   }
   j->max_rows = saved_max;
   unsigned long long n_owned = 0;
@@ -527,9 +625,7 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
   const int groups = (B >= 4 && P > 1) ? 2 : 1;
   for (int g = 0; g < groups; ++g) {
     const int b0 = g * B / groups, b1 = (g + 1) * B / groups;
-    pj_wait_kernel<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(j->block + lay.ready_off) + lay.flag_index(arena, b0, 0), (b1 - b0) * P, epoch,
-                                     j->d_err);
-    CC_CHECK_LAUNCH();
+    CC_TRY(wait_flags(j, ready_flag(j, j->rank, arena, b0, 0), (b1 - b0) * P, epoch, st));
     mark();
     SegIn seg;
     seg.counts = j->counts(arena) + lay.region_index(b0, 0, 0);
@@ -544,8 +640,7 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
   }
   pj_close_kernel<<<1, 32, 0, st>>>(d_result, cap, j->d_flag, j->d_err);
   CC_CHECK_LAUNCH();
-  pj_consumed_kernel<<<1, 32, 0, st>>>(peers_of(j), lay, j->rank, arena, epoch);
-  CC_CHECK_LAUNCH();
+  CC_TRY(signal_consumed(j, arena, epoch, st));
   if (trace) {
     mark();
     cudaStreamSynchronize(st);
