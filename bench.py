@@ -221,6 +221,7 @@ def workload_config(args) -> dict:
             "table": "linear_probing", "parallelism": f"hash-partition x{args.gpus}", "exchange": args.exchange, "sub_batches": args.sub_batches,
             "ce_probe": (args.ce_probe if args.ce_probe != "auto" else ("stream" if args.gpus <= 2 else "batch")) if args.exchange == "ce" else None,
             "copy_streams": args.copy_streams if args.exchange == "ce" else (4 if args.exchange == "cabi" else None),
+            "pipelined_across_steps": (not args.no_pipeline) if args.exchange == "cabi" else False,
             "l2_policy": "inputs far exceed L2; no flush needed"}
 
 
@@ -319,6 +320,8 @@ def main() -> int:
                          "or stream up to 2 GPUs and batch beyond (auto)")
     ap.add_argument("--copy-streams", type=int, default=4, help="N>1 with --exchange ce: copy streams the block copies of one shuffle are dealt over")
     ap.add_argument("--no-chain", action="store_true", help="N=1: skip the C3 join-chain sub-record")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="N>1 with --exchange cabi: one cc_pjoin_probe per step instead of begin(t + 1) + end(t) (the exchange of the next batch under the probe of this one)")
     ap.add_argument("--exchange", default="ce", choices=["ce", "cabi", "p2p", "nccl"],
                     help="N>1: copy-engine block copies under the probe (default), fused peer-memory scatter kernel, or NCCL all-to-all")
     args = ap.parse_args()
@@ -392,12 +395,28 @@ def main() -> int:
     recv_buf = torch.empty(cap, dtype=torch.int64, device=dev) if (distributed and args.exchange == "nccl") else None
     expected_sum = int(keys.sum().item()) & ((1 << 64) - 1)
 
+    in_flight = []  # cabi pipeline: a batch whose exchange is under way
+
+    def drain():
+        while in_flight:
+            in_flight.pop()
+            join.probe_end(out_key, out_payload, result[0])
+
     def step(k=None):
         k = keys if k is None else k
         if not distributed:
             return table.probe_batch(k, capacity=cap, out_key=out_key, out_payload=out_payload, result=result[0], sync=False)
         if args.exchange == "cabi":
-            return join.probe(k, out_key, out_payload, result[0])
+            if k is not keys or args.no_pipeline:  # (the end-to-end leg passes its own keys: one self-contained call)
+                drain()
+                return join.probe(k, out_key, out_payload, result[0])
+            # software pipelining across steps: a step enqueues the exchange of batch t + 1 and then probes batch t, which had the
+            # whole previous step to land; every step still does the full work of one batch (one partition + exchange, one probe)
+            if not in_flight:
+                join.probe_begin(k)
+                in_flight.append(1)
+            join.probe_begin(k)
+            return join.probe_end(out_key, out_payload, result[0])
         if args.exchange in ("p2p", "ce"):
             return join.probe_pipelined(k, n_sub, out_key, out_payload, result)
         shuffled = join.shuffle(k, out=recv_buf)
@@ -440,6 +459,8 @@ def main() -> int:
         step()
         b.record()
     t_all1.record()
+    if distributed and args.exchange == "cabi":
+        drain()  # the batch still in flight (its result equals every other step's: same keys)
     barrier()
     launches = pkg.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None

@@ -197,6 +197,8 @@ class Comm(C.Structure):
 SIGNATURES.update({
     "cc_pjoin_create": (_int, [_pvp, C.POINTER(Comm), _int, _vp, _sz, _sz, _int, _vp]),
     "cc_pjoin_probe": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "cc_pjoin_probe_begin": (_int, [_vp, _vp, _sz, _vp]),
+    "cc_pjoin_probe_end": (_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "cc_pjoin_table": (_int, [_vp, _pvp]),
     "cc_pjoin_destroy": (_int, [_vp]),
 })

@@ -33,6 +33,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda.h>  // types of the stream memory operations only: the entry points are resolved at run time, libcuda is not linked
@@ -206,6 +207,13 @@ struct cc_pjoin {
   cc_ht *table = nullptr;
   size_t n_build_total = 0, table_slots = 0;
   PjMemOps memops;                             // stream memory operations (empty: signal / wait with kernels)
+  struct Batch {
+    int arena;
+    unsigned long long epoch, call;
+  };
+  std::vector<Batch> begun;                    // probe batches whose exchange is under way (cc_pjoin_probe_begin .. _end)
+  unsigned long long calls = 0;
+  std::vector<std::pair<cudaEvent_t, std::string>> marks;  // CCB_PJ_TRACE
 
   int64_t *arena(int r, int a) const { return reinterpret_cast<int64_t *>(peer_block[r] + lay.data_off) + (size_t) a * lay.arena_rows(); }
   unsigned long long *counts(int a) const {
@@ -583,50 +591,85 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   return CC_OK;
 }
 
-int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity,
-                   cc_probe_result *d_result, cc_stream_t s) {
+// evidence switch CCB_PJ_TRACE=1: CUDA-event timeline of the calls on their stream (synchronises; printed by every rank)
+static bool pj_trace() {
+  static const bool on = [] {
+    const char *e = getenv("CCB_PJ_TRACE");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+static void pj_mark(cc_pjoin *j, cudaStream_t st, const char *name, int idx = -1) {
+  if (!pj_trace()) return;
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  cudaEventRecord(ev, st);
+  j->marks.push_back({ev, idx >= 0 ? std::string(name) + std::to_string(idx) : std::string(name)});
+}
+static void pj_print_trace(cc_pjoin *j, cudaStream_t st) {
+  if (!pj_trace() || j->marks.empty()) return;
+  cudaStreamSynchronize(st);
+  std::string line = "pjoin timeline rank " + std::to_string(j->rank) + " (ms since " + j->marks[0].second + ", " + std::to_string(j->pieces) + " pieces, " +
+                     std::to_string(j->slices) + " slices):";
+  for (size_t i = 1; i < j->marks.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, j->marks[0].first, j->marks[i].first);
+    char buf[64];
+    snprintf(buf, sizeof(buf), " %s=%.2f", j->marks[i].second.c_str(), ms);
+    line += buf;
+  }
+  fprintf(stderr, "%s\n", line.c_str());
+  for (auto &m : j->marks) cudaEventDestroy(m.first);
+  j->marks.clear();
+}
+
+int cc_pjoin_probe_begin(cc_pjoin *j, const int64_t *d_keys, size_t n, cc_stream_t s) {
   CC_TRY(require_device());
-  CC_REQUIRE(j && d_result, "NULL argument");
+  CC_REQUIRE(j, "NULL argument");
   CC_REQUIRE(n == 0 || d_keys, "d_keys is NULL");
   CC_REQUIRE(n <= j->max_rows * (size_t) j->pieces, "%zu probe rows exceed the %zu this join was sized for", n, j->max_rows * (size_t) j->pieces);
+  CC_REQUIRE(j->begun.size() < (size_t) kPjArenas, "at most %d probe batches can be in flight: call cc_pjoin_probe_end first", kPjArenas);
+  cudaStream_t st = as_stream(s);
+  const int B = j->pieces;
+  const int arena = (int) (j->uses % kPjArenas);
+  const unsigned long long epoch = j->uses / kPjArenas + 1;
+  ++j->uses;
+  pj_mark(j, st, "begin");
+  // EVERY rank sends B pieces per batch, whatever its own row count: the piece boundaries only depend on B
+  const size_t per = (n + B - 1) / B;
+  for (int b = 0; b < B; ++b) {
+    const size_t off = std::min(n, (size_t) b * per), cnt = std::min(per, n - off);
+    CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, j->slices, j->log2s, arena, b, epoch, b == 0, st));
+    pj_mark(j, st, "F", b);
+  }
+  j->begun.push_back({arena, epoch, j->calls++});
+  return CC_OK;
+}
+
+int cc_pjoin_probe_end(cc_pjoin *j, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity, cc_probe_result *d_result, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(j && d_result, "NULL argument");
+  CC_REQUIRE(!j->begun.empty(), "cc_pjoin_probe_end without a batch begun by cc_pjoin_probe_begin");
   cudaStream_t st = as_stream(s);
   const PjLayout &lay = j->lay;
   const int P = j->world, B = j->pieces, S = j->slices;
   const size_t cap = (d_out_key || d_out_payload) ? out_capacity : 0;
-  const int arena = (int) (j->uses % kPjArenas);
-  const unsigned long long epoch = j->uses / kPjArenas + 1;
-  ++j->uses;
-  // evidence switch CCB_PJ_TRACE=1: CUDA-event timeline of the call on `st` (synchronises; printed by every rank)
-  static const bool trace = [] {
-    const char *e = getenv("CCB_PJ_TRACE");
-    return e && e[0] == '1';
-  }();
-  std::vector<cudaEvent_t> marks;
-  auto mark = [&]() {
-    if (!trace) return;
-    cudaEvent_t ev;
-    cudaEventCreate(&ev);
-    cudaEventRecord(ev, st);
-    marks.push_back(ev);
-  };
-  mark();
-  // EVERY rank sends B pieces per call, whatever its own row count: the piece boundaries only depend on B
-  const size_t per = (n + B - 1) / B;
-  for (int b = 0; b < B; ++b) {
-    const size_t off = std::min(n, (size_t) b * per), cnt = std::min(per, n - off);
-    CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, S, j->log2s, arena, b, epoch, b == 0, st));
-    mark();
-  }
-  // The pieces are probed in (at most) two groups: the first half while the second half is still on its way -- the copy chain of
-  // the last pieces hides under the first probe at the price of streaming the table twice (+ table_bytes / HBM rate per step).
-  // Within a group the arena [piece][sender][slice] is walked slice by slice: all pieces and senders of one table slice, then the
-  // next slice.
+  const cc_pjoin::Batch batch = j->begun.front();
+  j->begun.erase(j->begun.begin());
+  const int arena = batch.arena;
+  const unsigned long long epoch = batch.epoch;
+  // A batch whose exchange had a whole later cc_pjoin_probe_begin to complete (software pipelining across steps) has landed: ONE
+  // probe, the table is streamed once.  A batch that was begun just now is probed in two groups of pieces: the first half while
+  // the second half is still on its way -- the copy chain of the last pieces hides under the first probe at the price of
+  // streaming the table twice.  Within a group the arena [piece][sender][slice] is walked slice by slice: all pieces and
+  // senders of one table slice, then the next slice.
+  const bool pipelined = !j->begun.empty();
   PJ_CUDA(cudaMemsetAsync(d_result, 0, sizeof(cc_probe_result), st));
-  const int groups = (B >= 4 && P > 1) ? 2 : 1;
+  const int groups = (!pipelined && B >= 4 && P > 1) ? 2 : 1;
   for (int g = 0; g < groups; ++g) {
     const int b0 = g * B / groups, b1 = (g + 1) * B / groups;
     CC_TRY(wait_flags(j, ready_flag(j, j->rank, arena, b0, 0), (b1 - b0) * P, epoch, st));
-    mark();
+    pj_mark(j, st, "WAIT", g);
     SegIn seg;
     seg.counts = j->counts(arena) + lay.region_index(b0, 0, 0);
     seg.cap = lay.cap;
@@ -636,32 +679,21 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
     seg.presliced = S > 1;
     CC_TRY(probe_segmented_device(j->table, j->arena(j->rank, arena) + lay.region_index(b0, 0, 0) * lay.cap, seg, d_out_key, d_out_payload, cap, d_result, st,
                                   /*accumulate=*/true));
-    mark();
+    pj_mark(j, st, "PROBE", g);
   }
   pj_close_kernel<<<1, 32, 0, st>>>(d_result, cap, j->d_flag, j->d_err);
   CC_CHECK_LAUNCH();
   CC_TRY(signal_consumed(j, arena, epoch, st));
-  if (trace) {
-    mark();
-    cudaStreamSynchronize(st);
-    std::string line = "pjoin timeline rank " + std::to_string(j->rank) + " (ms since begin, " + std::to_string(B) + " pieces, " + std::to_string(S) +
-                       " slices):";
-    for (size_t i = 1; i < marks.size(); ++i) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, marks[0], marks[i]);
-      char buf[64];
-      if (i <= (size_t) B)
-        snprintf(buf, sizeof(buf), " F%zu=%.2f", i - 1, ms);
-      else if (i + 1 == marks.size())
-        snprintf(buf, sizeof(buf), " END=%.2f", ms);
-      else
-        snprintf(buf, sizeof(buf), " %s%zu=%.2f", ((i - B) & 1) ? "WAIT" : "PROBE", (i - B - 1) / 2, ms);
-      line += buf;
-    }
-    fprintf(stderr, "%s\n", line.c_str());
-    for (auto ev : marks) cudaEventDestroy(ev);
-  }
+  pj_mark(j, st, "END");
+  pj_print_trace(j, st);
   return CC_OK;
+}
+
+int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity,
+                   cc_probe_result *d_result, cc_stream_t s) {
+  CC_REQUIRE(j && j->begun.empty(), "cc_pjoin_probe with a batch in flight (cc_pjoin_probe_begin without cc_pjoin_probe_end)");
+  CC_TRY(cc_pjoin_probe_begin(j, d_keys, n, s));
+  return cc_pjoin_probe_end(j, d_out_key, d_out_payload, out_capacity, d_result, s);
 }
 
 int cc_pjoin_table(const cc_pjoin *j, const cc_ht **ht) {

@@ -10,7 +10,7 @@
 // k is one of the generated keys), and the owner property of every result row.  --dump writes each rank's result rows for a
 // sorted-tuple comparison against the oracle (tests/test_gpu_multirank.py).
 //   pjoin_main --gpus 8 [--log2-build 20] [--log2-probe 22] [--table lp|chain] [--chunk-factor 1] [--hit 1] [--steps 3]
-//              [--sub-batches 4] [--dump prefix]
+//              [--sub-batches 4] [--pipeline 0|1] [--dump prefix]
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -29,7 +29,7 @@ static uint64_t mm64(uint64_t x) {  // hash_functions.h:8-16
 }
 
 int main(int argc, char **argv) {
-  int gpus = 1, log2_build = 20, log2_probe = 22, steps = 3, n_sub = 4;
+  int gpus = 1, log2_build = 20, log2_probe = 22, steps = 3, n_sub = 4, pipeline = 0;
   size_t cf = 1, hit = 1;
   std::string table = "lp", dump;
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -43,6 +43,7 @@ int main(int argc, char **argv) {
     else if (a == "--steps") steps = std::stoi(v);
     else if (a == "--sub-batches") n_sub = std::stoi(v);
     else if (a == "--dump") dump = v;
+    else if (a == "--pipeline") pipeline = std::stoi(v);
   }
   const size_t n_build = (size_t) 1 << log2_build, n_probe = (size_t) 1 << log2_probe;
   const int kind = table == "lp" ? CC_HT_LP : CC_HT_CHAIN;
@@ -66,14 +67,25 @@ int main(int argc, char **argv) {
     DeviceArray<Attribute> out_key(cap, false), out_payload(cap, false);
     DeviceArray<uint64_t> res(sizeof(cc_probe_result) / sizeof(uint64_t));
     double best = 1e30;
-    for (int s = 0; s < steps + 1; ++s) {  // one warm-up step
+    auto *result = reinterpret_cast<cc_probe_result *>(res.data());
+    if (pipeline) join.ProbeBegin(probe.data(), np);  // prologue: batch 0 is on its way
+    for (int s = 0; s < steps + 1; ++s) {             // one warm-up step
       comm.Barrier();
       auto t0 = std::chrono::steady_clock::now();
-      join.Probe(probe.data(), np, out_key.data(), out_payload.data(), cap, reinterpret_cast<cc_probe_result *>(res.data()));
+      if (pipeline) {  // a step = the exchange of batch t + 1 is enqueued, then batch t (which had a whole step to land) is probed
+        join.ProbeBegin(probe.data(), np);
+        join.ProbeEnd(out_key.data(), out_payload.data(), cap, result);
+      } else {
+        join.Probe(probe.data(), np, out_key.data(), out_payload.data(), cap, result);
+      }
       Check(cc_stream_sync(nullptr));
       comm.Barrier();  // a step ends when its slowest rank is done
       const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       if (s > 0 && dt < best) best = dt;
+    }
+    if (pipeline) {  // epilogue: the batch still in flight (same keys, same result)
+      join.ProbeEnd(out_key.data(), out_payload.data(), cap, result);
+      Check(cc_stream_sync(nullptr));
     }
     auto r = res.ToHost();
     // ---- host recomputation of this rank's SENT keys: count and checksums of the whole join are sums over the probe keys
@@ -129,9 +141,9 @@ int main(int argc, char **argv) {
       const bool ok = got[0] == exp[0] && got[1] == exp[1] && got[2] == exp[2] && overflow == 0 && owned == 1;
       cc_ht_info info = join.TableInfo();
       printf("{\"gpus\": %d, \"table\": \"%s\", \"n_build\": %zu, \"n_probe\": %zu, \"chunk_factor\": %zu, \"hit\": %zu, \"sub_batches\": %d, "
-             "\"n_matches\": %llu, \"key_sum\": %llu, \"payload_sum\": %llu, \"expected_matches\": %llu, \"overflow\": %llu, \"owner_property\": %s, "
+             "\"pipelined\": %d, \"n_matches\": %llu, \"key_sum\": %llu, \"payload_sum\": %llu, \"expected_matches\": %llu, \"overflow\": %llu, \"owner_property\": %s, "
              "\"checks_ok\": %s, \"ms_per_step\": %.3f, \"probe_tuples_per_sec\": %.4g, \"build_seconds\": %.3f, \"local_table_slots\": %zu}\n",
-             gpus, table.c_str(), n_build, n_probe, cf, hit, n_sub, (unsigned long long) got[0], (unsigned long long) got[1],
+             gpus, table.c_str(), n_build, n_probe, cf, hit, n_sub, pipeline, (unsigned long long) got[0], (unsigned long long) got[1],
              (unsigned long long) got[2], (unsigned long long) exp[0], (unsigned long long) overflow, owned ? "true" : "false", ok ? "true" : "false",
              worst * 1e3, n_probe / worst, build_s, (size_t) info.n_slots);
       if (!ok) rc = 3;

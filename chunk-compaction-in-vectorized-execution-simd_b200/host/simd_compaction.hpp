@@ -514,6 +514,11 @@ class PartitionedJoin {
   void Probe(const Attribute *d_keys, size_t n, Attribute *d_out_key, Attribute *d_out_payload, size_t out_capacity, cc_probe_result *d_result) {
     Check(cc_pjoin_probe(h_, d_keys, n, d_out_key, d_out_payload, out_capacity, d_result, nullptr));
   }
+  // the two halves, for software pipelining across steps: ProbeBegin(t + 1) may be called before ProbeEnd(t)
+  void ProbeBegin(const Attribute *d_keys, size_t n) { Check(cc_pjoin_probe_begin(h_, d_keys, n, nullptr)); }
+  void ProbeEnd(Attribute *d_out_key, Attribute *d_out_payload, size_t out_capacity, cc_probe_result *d_result) {
+    Check(cc_pjoin_probe_end(h_, d_out_key, d_out_payload, out_capacity, d_result, nullptr));
+  }
   cc_ht_info TableInfo() const {
     const cc_ht *t = nullptr;
     Check(cc_pjoin_table(h_, &t));

@@ -608,6 +608,20 @@ class CPartitionedJoin:
                                                            out_payload.data_ptr() if out_payload is not None else None, cap,
                                                            result.data_ptr(), torch.cuda.current_stream().cuda_stream))
 
+    def probe_begin(self, local_probe_keys: torch.Tensor) -> None:
+        """First half of a probe (cc_pjoin_probe_begin): partition + copies of this batch are enqueued.  May be called for batch
+        t + 1 before probe_end of batch t: the exchange then runs underneath the probe of the batch before it."""
+        n = local_probe_keys.numel()
+        self.pkg._lib.check(self.pkg.lib().cc_pjoin_probe_begin(self._h, local_probe_keys.data_ptr() if n else None, n,
+                                                                 torch.cuda.current_stream().cuda_stream))
+
+    def probe_end(self, out_key: Optional[torch.Tensor], out_payload: Optional[torch.Tensor], result: torch.Tensor) -> None:
+        """Second half (cc_pjoin_probe_end): waits for the oldest batch begun and probes it."""
+        cap = out_key.numel() if out_key is not None else (out_payload.numel() if out_payload is not None else 0)
+        self.pkg._lib.check(self.pkg.lib().cc_pjoin_probe_end(self._h, out_key.data_ptr() if out_key is not None else None,
+                                                               out_payload.data_ptr() if out_payload is not None else None, cap,
+                                                               result.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             h, self._h = self._h, None

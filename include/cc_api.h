@@ -454,6 +454,12 @@ int cc_pjoin_create(cc_pjoin **join, const cc_comm *comm, int kind, const int64_
  * peer never delivered (bounded wait timed out -- the join is unusable afterwards).  Nothing is synchronised.           */
 int cc_pjoin_probe(cc_pjoin *join, const int64_t *d_keys, size_t n, int64_t *d_out_key, int64_t *d_out_payload,
                    size_t out_capacity, cc_probe_result *d_result, cc_stream_t stream);
+/* The same in two halves, for software pipelining across steps: _begin enqueues partition + copies of a batch, _end waits
+ * for it and probes it.  begin(t + 1) may be called before end(t) (at most two batches in flight): the exchange of batch
+ * t + 1 then runs underneath the probe of batch t, and a batch that had that much time to land is probed in one pass.   */
+int cc_pjoin_probe_begin(cc_pjoin *join, const int64_t *d_keys, size_t n, cc_stream_t stream);
+int cc_pjoin_probe_end(cc_pjoin *join, int64_t *d_out_key, int64_t *d_out_payload, size_t out_capacity,
+                       cc_probe_result *d_result, cc_stream_t stream);
 int cc_pjoin_table(const cc_pjoin *join, const cc_ht **ht); /* this rank's table (cc_ht_get_info / export) */
 int cc_pjoin_destroy(cc_pjoin *join);                       /* collective */
 

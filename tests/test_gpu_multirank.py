@@ -52,7 +52,8 @@ def test_cpp_pjoin_driver_matches_oracle(ccb, tmp_path, world, table, cf, hit):
     if cf != 8:
         env["CCB_PJ_SLICE_BYTES"] = str(32 << 10)
     out = subprocess.run([PJOIN, "--gpus", str(world), "--log2-build", str(lb), "--log2-probe", str(lp), "--table", table, "--chunk-factor", str(cf),
-                          "--hit", str(hit), "--steps", "2", "--sub-batches", "5", "--dump", prefix], capture_output=True, text=True, timeout=600, env=env)
+                          "--hit", str(hit), "--steps", "2", "--sub-batches", "5", "--pipeline", "1" if table == "chain" else "0", "--dump", prefix],
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["checks_ok"] and r["owner_property"] and r["overflow"] == 0 and r["n_matches"] == r["expected_matches"]
