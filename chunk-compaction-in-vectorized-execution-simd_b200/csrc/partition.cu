@@ -93,9 +93,6 @@ __global__ void partition_offsets_kernel(const unsigned long long *__restrict__ 
 // [-kPartTile, 2^62): -1 is a legitimate value (it used to be the marker, which silently dropped such a run), 2^63 is not.
 constexpr unsigned long long kDroppedRun = 1ull << 63;
 
-struct ScatterDst {
-  int64_t *p[kMaxPeers];
-};
 
 // TMA == true: the NEXT tile of keys is pulled into shared memory by one cp.async.bulk (UBLKCP) while the
 // CTA ranks / sorts / stores the current one, so the key stream never waits behind the tile's barriers.
@@ -377,6 +374,25 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
   }
   if (d_prefix) CC_TRY(seg_prefix_device(d_cursors, parts, cap_rows, seg_tile, d_prefix, st));
   return CC_OK;
+}
+
+int partition_single_multi(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors, int *d_flag,
+                           int64_t *d_out, const ScatterDst *dsts, cudaStream_t st, bool sticky_flag) {
+  const int parts = fn.parts();
+  CC_CUDA(cudaMemsetAsync(d_cursors, 0, parts * sizeof(unsigned long long), st));
+  if (!sticky_flag) CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
+  if (blocks == 0) blocks = 1;
+  const int owners = fn.obits ? 1 << fn.obits : parts;
+  CC_REQUIRE(owners <= kMaxPeers, "redirected partitions need at most %d destinations", kMaxPeers);
+  ScatterDst dst;
+  bool any = false;
+  for (int o = 0; o < kMaxPeers; ++o) {
+    dst.p[o] = (o < owners && dsts && dsts->p[o]) ? dsts->p[o] : d_out;
+    any = any || dst.p[o] != d_out;
+  }
+  if (any) return launch_scatter<true>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, SegIn());
+  return launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, SegIn());
 }
 
 int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,

@@ -73,6 +73,11 @@ struct SegIn {
   }
 };
 
+// destination buffers of a scatter, one per OWNER (plain function: per partition): the peer scatter / the redirected partitions
+struct ScatterDst {
+  int64_t *p[kMaxPeers];
+};
+
 // histogram + offsets + scatter on `st`; d_counts/d_offsets/d_cursors hold P entries each
 // after_count (optional): an event slot recorded between the histogram and the scatter (phase timing)
 // gate (optional): every kernel of the sequence only runs when *gate != 0 (device-side fallback switch)
@@ -87,6 +92,11 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
                             int *d_flag, uint32_t seg_tile, uint32_t *d_prefix, int64_t *d_out, cudaStream_t st, SegIn seg = SegIn(),
                             bool accumulate = false, int self_part = -1, int64_t *d_self_out = nullptr, bool sticky_flag = false);
 // (a fused owner x slice function: self_part is the OWNER whose regions go to d_self_out)
+// The general form: owner o's regions go to dsts->p[o] (at the same region offsets as in d_out) wherever that is not NULL --
+// this rank's own arena, or a PEER's arena mapped over NVLink: the scatter kernel then stores those rows straight into the
+// owner's memory and no copy is needed for them.
+int partition_single_multi(const int64_t *d_keys, size_t n, PartFn fn, unsigned long long cap_rows, unsigned long long *d_cursors, int *d_flag,
+                           int64_t *d_out, const ScatterDst *dsts, cudaStream_t st, bool sticky_flag);
 // accumulate: keep cursors / flag of earlier calls (the regions fill up over several inputs)
 // d_prefix[0 .. parts] = exclusive prefix of ceil(min(d_cursors[p], cap_rows) / seg_tile) (the probe kernel's tile directory)
 int seg_prefix_device(const unsigned long long *d_cursors, int parts, unsigned long long cap_rows, uint32_t seg_tile, uint32_t *d_prefix,

@@ -44,9 +44,8 @@
 namespace ccb {
 
 constexpr int kPjArenas = 2;        // receive arenas, alternating between steps
-constexpr int kPjSendSlots = 3;     // rotating send buffers (one piece each)
-constexpr int kPjCopyStreams = 4;   // one stream drives one copy engine at a time
-constexpr int kPjMaxPieces = 16;
+constexpr int kPjMaxCopyStreams = 8; // one stream drives one copy engine at a time (CCB_PJ_COPY_STREAMS, default 4)
+constexpr int kPjMaxPieces = 16;    // = send slots: a whole batch is partitioned without ever waiting for its copies
 constexpr unsigned long long kPjSpinNs = 20ull * 1000 * 1000 * 1000;  // a wait gives up after 20 s (a peer died): error bit, no hang
 constexpr size_t kPjSliceBytes = 32u << 20;                           // target table bytes per slice (profiles/r1_sweep_slices.txt)
 constexpr size_t kPjSliceMinTable = 96u << 20;                        // smaller tables are probed directly (they live in L2 anyway)
@@ -197,12 +196,15 @@ struct cc_pjoin {
   PjLayout lay;
   unsigned char *block = nullptr;              // own exchange allocation: flags | counts | kPjArenas arenas
   unsigned char *peer_block[kMaxPeers] = {};   // every rank's allocation in this address space (own pointer at [rank])
-  int64_t *send[kPjSendSlots] = {};            // [owner][slice][cap]
-  unsigned long long *d_counts = nullptr;      // [kPjSendSlots][P * Sa] fill counts of the scatter
+  int n_slots = 1;                             // send slots (= pieces: the partition pass of a batch never waits for its copies)
+  int n_cs = 4;                                // copy streams in use
+  int n_direct = 0;                            // remote owners whose regions the scatter kernel stores straight into their arena
+  int64_t *send[kPjMaxPieces] = {};            // [owner][slice][cap]
+  unsigned long long *d_counts = nullptr;      // [n_slots][P * Sa] fill counts of the scatter
   int *d_flag = nullptr, *d_err = nullptr;     // sticky region-overrun flag, wait-timeout flag
-  cudaStream_t cs[kPjCopyStreams] = {};
-  cudaEvent_t parted[kPjSendSlots] = {}, copied[kPjSendSlots] = {}, gate = nullptr, joined[kPjCopyStreams] = {};
-  unsigned long long sends = 0;                // pieces sent so far (send slot = sends % kPjSendSlots)
+  cudaStream_t cs[kPjMaxCopyStreams] = {};
+  cudaEvent_t parted[kPjMaxPieces] = {}, copied[kPjMaxPieces] = {}, gate = nullptr, joined[kPjMaxCopyStreams] = {};
+  unsigned long long sends = 0;                // pieces sent so far (send slot = sends % n_slots)
   unsigned long long uses = 0;                 // arena uses so far (arena = uses % kPjArenas, its epoch = uses / kPjArenas + 1)
   cc_ht *table = nullptr;
   size_t n_build_total = 0, table_slots = 0;
@@ -306,43 +308,56 @@ int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, i
   const int P = j->world;
   const PjLayout &lay = j->lay;
   const unsigned long long k = j->sends++;
-  const int slot = (int) (k % kPjSendSlots);
+  const int slot = (int) (k % j->n_slots);
   unsigned long long *counts = j->d_counts + (size_t) slot * P * lay.Sa;
-  if (k >= (unsigned long long) kPjSendSlots) PJ_CUDA(cudaStreamWaitEvent(st, j->copied[slot], 0));  // the copies of piece k - 3 have left the slot
+  if (k >= (unsigned long long) j->n_slots) PJ_CUDA(cudaStreamWaitEvent(st, j->copied[slot], 0));  // the copies of piece k - n_slots have left the slot
   const PartFn fn = S > 1 ? PartFn::owner_and_slice(j->log2p, j->table_slots - 1, log2_floor_pj(j->table_slots), log2s)
                           : PartFn::high_bits(j->log2p);
-  // Region q = owner * S + slice sits at q * cap in the send slot.  The rows this rank keeps go straight into its own arena:
-  // there the same region lives at region_index(piece, rank, slice) * cap, so the redirect pointer is shifted accordingly.
-  int64_t *self = j->arena(j->rank, arena) + lay.region_index(piece, j->rank, 0) * lay.cap - (size_t) j->rank * S * lay.cap;
-  if (S != lay.Sa) {
-    // the arena's slice stride is the allocated one: a geometry with fewer slices (the build side: S == 1) cannot be written in
-    // place by the scatter kernel, it is copied like a peer's
-    self = nullptr;
+  // Region q = owner * S + slice sits at q * cap in the send slot.  In owner o's arena the same region lives at
+  // region_index(piece, rank, slice) * cap, so a pointer into an arena is shifted accordingly.  In place go: the rows this rank
+  // keeps, and the rows of the first n_direct remote owners (the scatter kernel stores them over NVLink itself -- SM stores and
+  // copy engines then share the exchange).  A geometry with fewer slices than allocated (the build side: S == 1) cannot be
+  // written in place: the arena's slice stride is the allocated one.
+  const bool in_place = S == lay.Sa && P > 1;
+  ScatterDst dsts;
+  bool direct[kMaxPeers];
+  for (int o = 0; o < kMaxPeers; ++o) {
+    dsts.p[o] = nullptr;
+    direct[o] = false;
   }
-  CC_TRY(partition_single_device(d_keys, n, fn, lay.cap, counts, j->d_flag, 0, nullptr, j->send[slot], st, SegIn(), false,
-                                 (self && P > 1) ? j->rank : -1, (self && P > 1) ? self : nullptr, /*sticky_flag=*/true));
+  if (in_place) {
+    for (int i = 0; i <= j->n_direct && i < P; ++i) {
+      const int o = (j->rank + i) % P;
+      dsts.p[o] = j->arena(o, arena) + lay.region_index(piece, j->rank, 0) * lay.cap - (size_t) o * S * lay.cap;
+      direct[o] = true;
+    }
+    // stores into a peer's arena: that owner must have consumed the arena's previous use BEFORE the kernel runs
+    if (first_of_use && epoch > 1 && j->n_direct > 0) CC_TRY(wait_flags(j, consumed_flag(j, j->rank, arena, 0), P, epoch - 1, st));
+  }
+  CC_TRY(partition_single_multi(d_keys, n, fn, lay.cap, counts, j->d_flag, j->send[slot], in_place ? &dsts : nullptr, st, /*sticky_flag=*/true));
   PJ_CUDA(cudaEventRecord(j->parted[slot], st));
   cudaStream_t c0 = j->cs[0];
   PJ_CUDA(cudaStreamWaitEvent(c0, j->parted[slot], 0));
   if (first_of_use && epoch > 1) CC_TRY(wait_flags(j, consumed_flag(j, j->rank, arena, 0), P, epoch - 1, c0));
   PJ_CUDA(cudaEventRecord(j->gate, c0));
-  for (int s = 1; s < kPjCopyStreams; ++s) PJ_CUDA(cudaStreamWaitEvent(j->cs[s], j->gate, 0));
+  for (int s = 1; s < j->n_cs; ++s) PJ_CUDA(cudaStreamWaitEvent(j->cs[s], j->gate, 0));
   // one stream drives one copy engine at a time and a single engine does not fill an NVLink 5 port (measured at P = 2 with one
   // copy per piece: 450 GB/s): with fewer destinations than copy streams every block is cut into chunks dealt over the streams
   const size_t rows = (size_t) S * lay.cap;
-  const int dests = (self && P > 1) ? P - 1 : P;
-  const int chunks = dests >= kPjCopyStreams ? 1 : (kPjCopyStreams + dests - 1) / dests;
+  int dests = 0;
+  for (int o = 0; o < P; ++o) dests += direct[o] ? 0 : 1;
+  const int chunks = (dests == 0 || dests >= j->n_cs) ? 1 : (j->n_cs + dests - 1) / dests;
   const size_t chunk_rows = ((rows + chunks - 1) / chunks + 511) / 512 * 512;
   int n_copy = 0;
   for (int i = 0; i < P; ++i) {
     const int o = (j->rank + i) % P;  // stagger the destinations so that the ranks do not all hit the same peer at once
-    if (o == j->rank && self && P > 1) continue;  // written in place by the scatter kernel
+    if (direct[o]) continue;          // written in place by the scatter kernel
     int64_t *dst = j->arena(o, arena) + lay.region_index(piece, j->rank, 0) * lay.cap;
     const int64_t *src = j->send[slot] + (size_t) o * rows;
     for (size_t at = 0; at < rows; at += chunk_rows)
-      PJ_CUDA(cudaMemcpyAsync(dst + at, src + at, std::min(chunk_rows, rows - at) * 8, cudaMemcpyDeviceToDevice, j->cs[n_copy++ % kPjCopyStreams]));
+      PJ_CUDA(cudaMemcpyAsync(dst + at, src + at, std::min(chunk_rows, rows - at) * 8, cudaMemcpyDeviceToDevice, j->cs[n_copy++ % j->n_cs]));
   }
-  for (int s = 1; s < kPjCopyStreams; ++s) {
+  for (int s = 1; s < j->n_cs; ++s) {
     PJ_CUDA(cudaEventRecord(j->joined[s], j->cs[s]));
     PJ_CUDA(cudaStreamWaitEvent(c0, j->joined[s], 0));
   }
@@ -459,18 +474,27 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   lay.finish();
   cudaError_t e = cudaMalloc(&j->block, lay.total);
   if (e == cudaSuccess) e = cudaMemset(j->block, 0, lay.data_off);
-  for (int b = 0; b < kPjSendSlots && e == cudaSuccess; ++b) e = cudaMalloc(&j->send[b], (size_t) P * S * lay.cap * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&j->d_counts, (size_t) kPjSendSlots * P * S * sizeof(unsigned long long));
+  j->n_slots = std::max(n_sub, 2);
+  auto env_int = [](const char *name, int dflt, int lo, int hi) {
+    const char *v = getenv(name);
+    if (!v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+  };
+  j->n_cs = env_int("CCB_PJ_COPY_STREAMS", 4, 1, kPjMaxCopyStreams);      // measurement switches, see DESIGN.md
+  j->n_direct = env_int("CCB_PJ_DIRECT", 0, 0, P - 1);                    // remote owners served by the scatter kernel's own NVLink stores
+  for (int b = 0; b < j->n_slots && e == cudaSuccess; ++b) e = cudaMalloc(&j->send[b], (size_t) P * S * lay.cap * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&j->d_counts, (size_t) j->n_slots * P * S * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&j->d_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&j->d_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(j->d_flag, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(j->d_err, 0, sizeof(int));
-  for (int i = 0; i < kPjCopyStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&j->cs[i], cudaStreamNonBlocking);
-  for (int i = 0; i < kPjSendSlots && e == cudaSuccess; ++i) {
+  for (int i = 0; i < j->n_cs && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&j->cs[i], cudaStreamNonBlocking);
+  for (int i = 0; i < j->n_slots && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&j->parted[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->copied[i], cudaEventDisableTiming);
   }
-  for (int i = 0; i < kPjCopyStreams && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&j->joined[i], cudaEventDisableTiming);
+  for (int i = 0; i < j->n_cs && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&j->joined[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->gate, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
