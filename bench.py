@@ -322,8 +322,9 @@ def main() -> int:
     ap.add_argument("--no-chain", action="store_true", help="N=1: skip the C3 join-chain sub-record")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="N>1 with --exchange cabi: one cc_pjoin_probe per step instead of begin(t + 1) + end(t) (the exchange of the next batch under the probe of this one)")
-    ap.add_argument("--exchange", default="ce", choices=["ce", "cabi", "p2p", "nccl"],
-                    help="N>1: copy-engine block copies under the probe (default), fused peer-memory scatter kernel, or NCCL all-to-all")
+    ap.add_argument("--exchange", default="cabi", choices=["cabi", "ce", "p2p", "nccl"],
+                    help="N>1: the C-ABI join (cc_pjoin_*: fused owner x slice partition on the sender, copy engines, device-side flags; default), "
+                         "the round-1 copy-engine pipeline on torch.distributed, fused peer-memory scatter kernel, or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
@@ -332,7 +333,7 @@ def main() -> int:
     if args.log2_probe is None:
         args.log2_probe = 31 if args.gpus == 1 else 30
     if args.sub_batches is None:
-        args.sub_batches = (8 if args.exchange == "cabi" else 4) if (args.gpus > 1 and args.exchange in ("ce", "cabi")) else 1
+        args.sub_batches = 4 if (args.gpus > 1 and args.exchange in ("ce", "cabi")) else 1
     if args.impl == "reference":
         return run_reference_arm(args)
 
