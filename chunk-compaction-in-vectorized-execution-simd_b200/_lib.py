@@ -183,6 +183,7 @@ SIGNATURES = {
     "cc_ipc_export": (_int, [_vp, _vp]),
     "cc_ipc_open": (_int, [_vp, _pvp]),
     "cc_ipc_close": (_int, [_vp]),
+    "cc_peer_copy_sm": (_int, [_vp, _vp, _sz, _int, _vp]),
 }
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)

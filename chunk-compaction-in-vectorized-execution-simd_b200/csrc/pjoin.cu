@@ -176,6 +176,21 @@ __global__ void pj_advance_kernel(const unsigned long long *__restrict__ counts,
   }
 }
 
+// SM-driven block copy (the alternative to a copy engine for peer memory): `blocks` CTAs stream src -> dst with 16-byte loads and
+// stores, 8 per thread in flight.  Measurement tool for the NVLink store rate of the SMs (tools/nvlink_bench.py).
+__global__ void __launch_bounds__(256) pj_sm_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 7 * stride < n16; i += 8 * stride) {
+    uint4 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldg(src + i + q * stride);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[i + q * stride] = v[q];
+  }
+  for (; i < n16; i += stride) dst[i] = __ldg(src + i);
+}
+
 __global__ void pj_close_kernel(cc_probe_result *res, size_t cap, int *region_flag, int *err) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     res->overflow = (res->n_matches > cap ? 1 : 0) | (*region_flag ? 2 : 0) | (*err ? 4 : 0);
@@ -718,6 +733,15 @@ int cc_pjoin_probe(cc_pjoin *j, const int64_t *d_keys, size_t n, int64_t *d_out_
   CC_REQUIRE(j && j->begun.empty(), "cc_pjoin_probe with a batch in flight (cc_pjoin_probe_begin without cc_pjoin_probe_end)");
   CC_TRY(cc_pjoin_probe_begin(j, d_keys, n, s));
   return cc_pjoin_probe_end(j, d_out_key, d_out_payload, out_capacity, d_result, s);
+}
+
+int cc_peer_copy_sm(void *d_dst, const void *d_src, size_t bytes, int blocks, cc_stream_t s) {
+  CC_TRY(require_device());
+  CC_REQUIRE(d_dst && d_src && bytes % 16 == 0 && blocks >= 1, "NULL pointer, size not a multiple of 16, or no blocks");
+  CC_REQUIRE(((uintptr_t) d_dst & 15) == 0 && ((uintptr_t) d_src & 15) == 0, "pointers must be 16-byte aligned");
+  pj_sm_copy_kernel<<<blocks, 256, 0, as_stream(s)>>>(static_cast<uint4 *>(d_dst), static_cast<const uint4 *>(d_src), bytes / 16);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
 }
 
 int cc_pjoin_table(const cc_pjoin *j, const cc_ht **ht) {

@@ -423,6 +423,9 @@ typedef struct {
 int cc_ipc_export(void *d_ptr, cc_ipc_handle *out);
 int cc_ipc_open(const cc_ipc_handle *handle, void **d_ptr);
 int cc_ipc_close(void *d_ptr);
+/* Block copy driven by `blocks` CTAs instead of a copy engine (16-byte loads / stores): the way to measure what the SMs can
+ * push into peer memory over NVLink (tools/nvlink_bench.py); d_dst may be a cc_ipc_open mapping.                         */
+int cc_peer_copy_sm(void *d_dst, const void *d_src, size_t bytes, int blocks, cc_stream_t stream);
 
 /* ------------------------------------------- partitioned multi-GPU join (C5) */
 /* The hash-partitioned join of SURVEY 8e behind the C ABI: one process per GPU, no collective library on the data path.
