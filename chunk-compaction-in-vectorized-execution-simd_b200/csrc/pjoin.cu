@@ -45,7 +45,7 @@ namespace ccb {
 
 constexpr int kPjArenas = 2;        // receive arenas, alternating between steps
 constexpr int kPjMaxCopyStreams = 8; // one stream drives one copy engine at a time (CCB_PJ_COPY_STREAMS, default 4)
-constexpr int kPjMaxPieces = 16;    // = send slots: a whole batch is partitioned without ever waiting for its copies
+constexpr int kPjMaxPieces = 16;    // pieces per batch; send slots = 2 x pieces: a batch is partitioned without waiting for the copies of the one before
 constexpr unsigned long long kPjSpinNs = 20ull * 1000 * 1000 * 1000;  // a wait gives up after 20 s (a peer died): error bit, no hang
 constexpr size_t kPjSliceBytes = 32u << 20;                           // target table bytes per slice (profiles/r1_sweep_slices.txt)
 constexpr size_t kPjSliceMinTable = 96u << 20;                        // smaller tables are probed directly (they live in L2 anyway)
@@ -214,11 +214,11 @@ struct cc_pjoin {
   int n_slots = 1;                             // send slots (= pieces: the partition pass of a batch never waits for its copies)
   int n_cs = 4;                                // copy streams in use
   int n_direct = 0;                            // remote owners whose regions the scatter kernel stores straight into their arena
-  int64_t *send[kPjMaxPieces] = {};            // [owner][slice][cap]
+  int64_t *send[2 * kPjMaxPieces] = {};        // [owner][slice][cap]
   unsigned long long *d_counts = nullptr;      // [n_slots][P * Sa] fill counts of the scatter
   int *d_flag = nullptr, *d_err = nullptr;     // sticky region-overrun flag, wait-timeout flag
   cudaStream_t cs[kPjMaxCopyStreams] = {};
-  cudaEvent_t parted[kPjMaxPieces] = {}, copied[kPjMaxPieces] = {}, gate = nullptr, joined[kPjMaxCopyStreams] = {};
+  cudaEvent_t parted[2 * kPjMaxPieces] = {}, copied[2 * kPjMaxPieces] = {}, gate = nullptr, joined[kPjMaxCopyStreams] = {};
   unsigned long long sends = 0;                // pieces sent so far (send slot = sends % n_slots)
   unsigned long long uses = 0;                 // arena uses so far (arena = uses % kPjArenas, its epoch = uses / kPjArenas + 1)
   cc_ht *table = nullptr;
@@ -489,7 +489,9 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   lay.finish();
   cudaError_t e = cudaMalloc(&j->block, lay.total);
   if (e == cudaSuccess) e = cudaMemset(j->block, 0, lay.data_off);
-  j->n_slots = std::max(n_sub, 2);
+  // two batches' worth of send slots: with the probe split in begin / end a batch is partitioned while the copies of the batch
+  // before it are still draining (copy engines run at about half their idle rate under the kernels: profiles/r2_nvlink_bench_n2.txt)
+  j->n_slots = 2 * n_sub;
   auto env_int = [](const char *name, int dflt, int lo, int hi) {
     const char *v = getenv(name);
     if (!v) return dflt;
