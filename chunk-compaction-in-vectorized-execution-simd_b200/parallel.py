@@ -622,6 +622,70 @@ class CPartitionedJoin:
                                                                out_payload.data_ptr() if out_payload is not None else None, cap,
                                                                result.data_ptr(), torch.cuda.current_stream().cuda_stream))
 
+    def probe_host(self, h_keys: torch.Tensor, h_out_key: torch.Tensor, h_out_payload: torch.Tensor, n_chunks: int = 4) -> int:
+        """End to end with HOST buffers (pinned int64 tensors; collective): this rank's probe keys travel host -> device in n_chunks
+        chunks, every chunk is one batch of the C-ABI join (begin / end, pipelined two deep: the exchange of chunk c + 1 runs under
+        the probe of chunk c), and the rows of chunk c go back to the host -- on their own stream, as soon as its 32-byte result
+        record has landed in pinned memory -- while the later chunks are still being copied in, exchanged and probed.  Returns the
+        number of rows this rank owns (rows [0, n) of h_out_key / h_out_payload)."""
+        n = h_keys.numel()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        per = -(-n // n_chunks) if n else 0
+        capc = per + per // 8 + (1 << 16)  # rows a rank can end up owning from one chunk (hash partition: per +- a fraction of a percent)
+        ws = getattr(self, "_host_ws", None)
+        if ws is None or ws["per"] < per or ws["n_chunks"] != n_chunks:
+            ws = {"per": per, "n_chunks": n_chunks, "dk": torch.empty(max(n, 1), dtype=torch.int64, device=dev),
+                  "ok": [torch.empty(capc, dtype=torch.int64, device=dev) for _ in range(n_chunks)],
+                  "op": [torch.empty(capc, dtype=torch.int64, device=dev) for _ in range(n_chunks)],
+                  "res": torch.zeros((n_chunks, 4), dtype=torch.int64, device=dev),
+                  "hres": torch.zeros((n_chunks, 4), dtype=torch.int64).pin_memory(),
+                  "s_in": torch.cuda.Stream(), "s_out": torch.cuda.Stream()}
+            self._host_ws = ws
+        dk, res, hres, s_in, s_out = ws["dk"], ws["res"], ws["hres"], ws["s_in"], ws["s_out"]
+        main = torch.cuda.current_stream()
+        s_in.wait_stream(main)
+        bounds = [(min(n, c * per), min(n, (c + 1) * per)) for c in range(n_chunks)]
+        ready = []
+        with torch.cuda.stream(s_in):
+            for lo, hi in bounds:
+                if hi > lo:
+                    dk[lo:hi].copy_(h_keys[lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ready.append(e)
+        done = []
+
+        def begin(c):
+            main.wait_event(ready[c])
+            lo, hi = bounds[c]
+            self.probe_begin(dk[lo:hi])
+
+        def end(c):
+            self.probe_end(ws["ok"][c], ws["op"][c], res[c])
+            hres[c].copy_(res[c], non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(main)
+            done.append(e)
+
+        begin(0)
+        for c in range(n_chunks):
+            if c + 1 < n_chunks:
+                begin(c + 1)
+            end(c)
+        hcap = min(h_out_key.numel(), h_out_payload.numel())
+        off = 0
+        for c, e in enumerate(done):
+            e.synchronize()  # the 32-byte record of chunk c is in pinned memory
+            m = min(int(hres[c, 0]), ws["ok"][c].numel(), hcap - off)
+            if m > 0:
+                s_out.wait_event(e)
+                with torch.cuda.stream(s_out):
+                    h_out_key[off:off + m].copy_(ws["ok"][c][:m], non_blocking=True)
+                    h_out_payload[off:off + m].copy_(ws["op"][c][:m], non_blocking=True)
+            off += max(m, 0)
+        s_out.synchronize()
+        return off
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             h, self._h = self._h, None

@@ -161,6 +161,15 @@ def main() -> int:
                         if join is not None and join.copier is not None:
                             join.copier.check_overflow()
                         rr = res.cpu().numpy().view(np.uint64)
+                        host_ok = True
+                        if exchange == "cabi" or (exchange == "ce" and plan == "partition"):
+                            # the host-buffer path of the same join (pinned keys in, the rows this rank owns out): same rows
+                            hk = my_probe.cpu().pin_memory()
+                            hok = torch.empty(cap, dtype=torch.int64).pin_memory()
+                            hop = torch.empty(cap, dtype=torch.int64).pin_memory()
+                            m_host = cjoin.probe_host(hk, hok, hop) if exchange == "cabi" else join.probe_host(hk, hok, hop, n_sub=n_sub)
+                            m_dev = int(rr[:, 0].sum())
+                            host_ok = m_host == m_dev and int(hok[:m_host].sum()) & U64 == int(rr[:, 1].sum()) & U64 and bool((hok[:m_host] == hop[:m_host]).all())
                         dense = n_sub == 1 or (exchange == "ce" and ce_probe == "stream") or exchange == "cabi"
                         capb = cap // n_sub
                         if dense:
@@ -187,7 +196,7 @@ def main() -> int:
                                        f"{'ok' if same_sums else 'MISMATCH'}  sorted tuples {'ok' if same_rows else 'MISMATCH'}")
                         else:
                             good = overflow == 0
-                        good = all_ok(good and own_p and own_b, dev)
+                        good = all_ok(good and own_p and own_b and host_ok, dev)
                         say(f"{'PASS' if good else 'FAIL'}  {tag}  {verdict}  owner property (probe rows, table keys) on every rank "
                             f"{'ok' if good or (own_p and own_b) else 'VIOLATED'}")
                         if not good:
