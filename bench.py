@@ -545,6 +545,10 @@ def main() -> int:
                 line["chain"] = chain_record(pkg, torch, peak)
             except Exception as e:  # noqa: BLE001 -- a sub-record never costs the headline line
                 line["chain"] = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                line["small_configs"] = small_config_records(pkg, torch, peak)
+            except Exception as e:  # noqa: BLE001
+                line["small_configs"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_e2e and not distributed:
         ne = 1 << min(args.e2e_log2_probe, args.log2_probe)
         hk = torch.empty(ne, dtype=torch.int64).pin_memory()
@@ -660,6 +664,52 @@ def chain_record(pkg, torch, peak, reps=5):
                             "roofline": {"bound": "hbm", "achieved": 8 * J * lhs_n / wall_ms / 1e6, "peak": peak, "unit": "GB/s", "frac": 8 * J * lhs_n / wall_ms / 1e6 / peak}})
         del tables
     return rec
+
+
+def small_config_records(pkg, torch, peak, reps=5):
+    """N = 1 sub-records for BASELINE configs 1 and 2, through cc_probe_batch with dense key + payload output:
+    C1 = single LP join, the reference's `simd_bench --scale 3` table (1024 build keys, 2048-tuple chunks on the CPU side) and a
+    main.cpp-sized one (2 M build keys), 2^27 probe keys; C2 = separate-chaining table, 2 M build keys, chunk_factor (fanout)
+    1 / 2 / 4 / 8, 20 M probe keys, every sparse match vector compacted into dense output rows.  Probe keys: counter generator
+    (murmurhash64(seed + i) & mask).  Checked: every probe key k matches chunk_factor build rows iff k is a generated build key.
+    Roofline: 8 B read + 16 B written per result row (the tables live in L2)."""
+    recs = []
+
+    def run(name, T, n_build, cf, n_probe, mask):
+        tab = T(n_build, cf)
+        keys = pkg.gen_keys_counter(n_probe, 5, mask)
+        num_unique = -(-n_build // cf)
+        step = n_build // num_unique
+        hit = ((keys % step) == 0) & ((keys // step) < num_unique)
+        copies = torch.clamp(n_build - (keys // step) * cf, max=cf)  # the last key's copies may be cut at n_build rows
+        want = int((copies * hit).sum().item())
+        want_sum = int((keys * copies * hit).sum().item()) & ((1 << 64) - 1)
+        del hit, copies
+        cap = want + 1024
+        ok = torch.empty(cap, dtype=torch.int64, device="cuda")
+        op = torch.empty(cap, dtype=torch.int64, device="cuda")
+        res = torch.zeros(4, dtype=torch.int64, device="cuda")
+        ts = []
+        for _ in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            tab.probe_batch(keys, capacity=cap, out_key=ok, out_payload=op, result=res, sync=False)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        r = [int(x) & ((1 << 64) - 1) for x in res.cpu().tolist()]
+        assert r[0] == want and r[1] == want_sum and r[2] == want_sum and r[3] == 0, (name, r, want, want_sum)
+        ms = statistics.mean(ts[1:])
+        gbs = (8 * n_probe + 16 * want) / ms / 1e6
+        recs.append({"config": name, "ms": ms, "probe_tuples_per_sec": n_probe / ms * 1e3, "result_rows": want,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}})
+
+    run("C1(i): LP, 1024 build keys (simd_bench --scale 3), 2^27 probe keys, hit 1", pkg.LPHashTable, 1024, 1, 1 << 27, 1023)
+    run("C1(i): LP, 1024 build keys (simd_bench --scale 3), 2^27 probe keys, hit 2", pkg.LPHashTable, 1024, 1, 1 << 27, 2047)
+    run("C1(ii): LP, 2^21 build keys, 2^27 probe keys, hit 1", pkg.LPHashTable, 1 << 21, 1, 1 << 27, (1 << 21) - 1)
+    for cf in (1, 2, 4, 8):
+        run(f"C2: chaining, 2^21 build keys, fanout {cf} (hit rate 1/{cf}), 20 M probe keys, dense output", pkg.HashTable, 1 << 21, cf, 20_000_000, (1 << 21) - 1)
+    return recs
 
 
 def load_traffic():
