@@ -647,18 +647,21 @@ def chain_record(pkg, torch, peak, reps=5):
                                 "roofline": {"bound": "hbm", "achieved": 8 * J * lhs_n / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": 8 * J * lhs_n / ms / 1e6 / peak}})
         # negative-feedback policy: one bandit per join picks the threshold of every batch; timed in steady state (the bandits keep
         # their state over `reps` passes over the LHS table, the last pass is the one reported)
+        # Batches must be large: a batch is one kernel, and a pipeline instance needs many chunks for its load to even out (one LHS
+        # row that matches at every level fans out to chunk_factor^4 result rows, all handled by the instance that pulled it).
         tuner = pkg.CompactTuner()
         for l in range(J):
             tuner.Initialize(0x1000 + l)
-        batch = 1 << 18
-        for i in range(3):
+        batch, passes = 1 << 21, 12  # 10 batches per pass; 120 pulls per bandit (its forced round-robin warm-up is 36)
+        for i in range(passes):
             t0 = time.perf_counter()
             d = pkg.chain_execute_tuned(tables, cols, tuner, batch)
             torch.cuda.synchronize()
             wall_ms = (time.perf_counter() - t0) * 1e3
         assert d["n_tuples"] == want_tuples and d["probe_tuples"] == want_probe, ("tuned", cf, d["n_tuples"], want_tuples)
         dev_ms = d["device_ns"] / 1e6
-        rec["runs"].append({"chunk_factor": cf, "policy": f"negative-feedback bandits (batches of {batch} LHS rows, third pass)", "ms": wall_ms, "device_ms": dev_ms,
+        rec["runs"].append({"chunk_factor": cf, "policy": f"negative-feedback bandits (batches of {batch} LHS rows, pass {passes} of {passes} over the LHS table)", "ms": wall_ms,
+                            "device_ms": dev_ms,
                             "probe_tuples_per_sec": want_probe / wall_ms * 1e3, "lhs_rows_per_sec": lhs_n / wall_ms * 1e3, "result_tuples": want_tuples,
                             "probe_tuples": want_probe,
                             "roofline": {"bound": "hbm", "achieved": 8 * J * lhs_n / wall_ms / 1e6, "peak": peak, "unit": "GB/s", "frac": 8 * J * lhs_n / wall_ms / 1e6 / peak}})

@@ -100,7 +100,7 @@ constexpr unsigned long long kDroppedRun = 1ull << 63;
 #ifndef CCB_SCATTER_ABLATE
 #define CCB_SCATTER_ABLATE 0
 #endif
-template <bool PEERS, bool TMA>
+template <bool PEERS, bool TMA, bool FUSED>
 __global__ void __launch_bounds__(kPartThreads, 2)
     partition_scatter_kernel(const int64_t *__restrict__ keys, size_t n, PartFn fn, const unsigned long long *__restrict__ offsets,
                              unsigned long long *cursors, ScatterDst dst, unsigned long long cap_rows, int *flag, int gated, SegIn seg) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kPartThreads, 2)
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
       if (FULL) {
-        p[j] = fn(k[j]);
+        p[j] = fn.template id<FUSED>(k[j]);
 #if CCB_SCATTER_ABLATE == 3
         r[j] = (uint32_t) j;
         if (j == 0 && threadIdx.x < (unsigned) parts) s_cnt[threadIdx.x] = kPartTile / parts;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kPartThreads, 2)
 #endif
       } else {
         bool ok = (uint32_t) (j * kPartThreads) + threadIdx.x < tile_n;
-        p[j] = ok ? fn(k[j]) : 0xFFFFFFFFu;
+        p[j] = ok ? fn.template id<FUSED>(k[j]) : 0xFFFFFFFFu;
         r[j] = ok ? atomicAdd(&s_cnt[p[j]], 1u) : 0;
       }
     }
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(kPartThreads, 2)
       for (int j = 0; j < kPartItems; ++j) {
         const uint32_t i = (uint32_t) (j * kPartThreads) + threadIdx.x;
         const uint64_t key = s_sorted[i];
-        const uint32_t pp = fn(key);
-        int64_t *out = PEERS ? dst.p[pp >> fn.sbits] : dst.p[0];
+        const uint32_t pp = fn.template id<FUSED>(key);
+        int64_t *out = PEERS ? dst.p[FUSED ? pp >> fn.sbits : pp] : dst.p[0];
         const unsigned long long d = s_delta[pp];
 #if CCB_SCATTER_ABLATE == 1
         if (d == kDroppedRun + 12345 + key) out[d + i] = (int64_t) key;
@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(kPartThreads, 2)
     } else {
       for (uint32_t i = threadIdx.x; i < tile_n; i += kPartThreads) {
         const uint64_t key = s_sorted[i];
-        const uint32_t pp = fn(key);
-        int64_t *out = PEERS ? dst.p[pp >> fn.sbits] : dst.p[0];
+        const uint32_t pp = fn.template id<FUSED>(key);
+        int64_t *out = PEERS ? dst.p[FUSED ? pp >> fn.sbits : pp] : dst.p[0];
         unsigned long long d = s_delta[pp];
         if (d != kDroppedRun) out[d + i] = (int64_t) key;
       }
@@ -306,13 +306,16 @@ static int launch_scatter(const int64_t *d_keys, size_t n, PartFn fn, const unsi
   }();
   const bool tma = !no_tma && (reinterpret_cast<uintptr_t>(d_keys) & 15) == 0;  // bulk copies need 16-byte alignment
   const size_t smem = (tma ? 2 : 1) * (size_t) kPartTile * sizeof(uint64_t);
-  if (tma) {
-    CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    partition_scatter_kernel<PEERS, true><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated, seg);
-  } else {
-    CC_CUDA(cudaFuncSetAttribute(partition_scatter_kernel<PEERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    partition_scatter_kernel<PEERS, false><<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated, seg);
-  }
+  auto go = [&](auto kernel) -> int {
+    CC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kernel<<<(unsigned) blocks, kPartThreads, smem, st>>>(d_keys, n, fn, d_offsets, d_cursors, dst, cap_rows, flag, gated, seg);
+    return CC_OK;
+  };
+  const bool fused = fn.obits != 0;  // owner x slice function (pjoin.cu)
+  if (tma)
+    CC_TRY(fused ? go(partition_scatter_kernel<PEERS, true, true>) : go(partition_scatter_kernel<PEERS, true, false>));
+  else
+    CC_TRY(fused ? go(partition_scatter_kernel<PEERS, false, true>) : go(partition_scatter_kernel<PEERS, false, false>));
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -365,7 +368,7 @@ int partition_single_device(const int64_t *d_keys, size_t n, PartFn fn, unsigned
   if (self_part >= 0 && d_self_out) {
     // one partition goes to a different buffer at the same region offset (the copy-engine exchange: the rows this rank keeps
     // are written straight into its own receive buffer instead of being copied there afterwards)
-    const int owners = fn.obits ? 1 << fn.obits : parts;  // plain function: every partition is an "owner" (sbits == 0)
+    const int owners = (fn.obits || fn.sbits) ? 1 << fn.obits : parts;  // plain function: every partition is an "owner"
     CC_REQUIRE(owners <= kMaxPeers && self_part < owners, "a redirected partition needs at most %d destinations", kMaxPeers);
     for (int p = 0; p < owners; ++p) dst.p[p] = p == self_part ? d_self_out : d_out;
     CC_TRY(launch_scatter<true>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, seg));
@@ -383,14 +386,14 @@ int partition_single_multi(const int64_t *d_keys, size_t n, PartFn fn, unsigned 
   if (!sticky_flag) CC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   size_t blocks = std::min<size_t>((n + kPartTile - 1) / kPartTile, (size_t) sm_count() * 4);
   if (blocks == 0) blocks = 1;
-  const int owners = fn.obits ? 1 << fn.obits : parts;
-  CC_REQUIRE(owners <= kMaxPeers, "redirected partitions need at most %d destinations", kMaxPeers);
+  const int owners = (fn.obits || fn.sbits) ? 1 << fn.obits : parts;  // a slice-only function (one rank) has ONE owner
   ScatterDst dst;
   bool any = false;
   for (int o = 0; o < kMaxPeers; ++o) {
     dst.p[o] = (o < owners && dsts && dsts->p[o]) ? dsts->p[o] : d_out;
     any = any || dst.p[o] != d_out;
   }
+  CC_REQUIRE(!any || owners <= kMaxPeers, "redirected partitions need at most %d destinations", kMaxPeers);
   if (any) return launch_scatter<true>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, SegIn());
   return launch_scatter<false>(d_keys, n, fn, nullptr, d_cursors, dst, blocks, st, cap_rows, d_flag, 0, SegIn());
 }
