@@ -392,7 +392,9 @@ static int build_lp(cc_ht *ht, const int64_t *d_keys, size_t n, int flags, cudaS
         }
       }
     }
-    int grid = launch_grid(n, 256, 16);
+    // streaming build: only as many CTAs as are resident at once (8 x 256 threads per SM) -- a second wave of CTAs would walk all
+    // the slices a second time
+    int grid = launch_grid(n, 256, scratch ? 8 : 16);
     if (flags & CC_BUILD_UNORDERED)
       lp_insert_unordered_kernel<<<grid, 256, 0, st>>>(keys_in, n, ht->d_slots, ht->mask, d_flags);
     else

@@ -311,9 +311,12 @@ int cc_compactor_destroy(cc_compactor *c);
 
 /* ------------------------------------------------------ fused join chain */
 /* ExecutePipeline + FlushPipelineCache (main.cpp:119-191) for a whole LHS table
- * in ONE persistent kernel: every CTA pulls 2048-row chunks, probes level 0,
- * compacts matches into a shared-memory chunk, runs level 1 on it once it holds
- * >= thresholds[0] rows, and so on (depth-first, like the reference recursion).
+ * in ONE persistent kernel: every pipeline instance (one warp; 40 per SM) pulls
+ * 64-row chunks of the LHS table, probes level 0, compacts the matches into a
+ * shared-memory chunk, runs level 1 on it once it holds enough rows for its
+ * threshold, and so on (depth-first, like the reference recursion).  Thresholds
+ * are expressed on the CC_CHAIN_WIDTH = 512-row scale whatever the instance's
+ * own chunk width W is: it waits for ceil(threshold * W / 512) rows.
  *   h_tables[n_joins]        one table per level
  *   h_lhs_cols[n_joins]      device column pointers of the LHS table (columnar)
  *   thresholds[n_joins]      thresholds[L] = compaction threshold of the compactor that sits
