@@ -191,6 +191,25 @@ __global__ void __launch_bounds__(256) pj_sm_copy_kernel(uint4 *__restrict__ dst
   for (; i < n16; i += stride) dst[i] = __ldg(src + i);
 }
 
+// The SM-driven tail of a piece's block copies (see cc_pjoin::sm_pct): up to kMaxPeers jobs, all CTAs of the grid stream through
+// the concatenation of the jobs with 16-byte loads / stores.
+struct PjCopyJobs {
+  uint4 *dst[kMaxPeers];
+  const uint4 *src[kMaxPeers];
+  unsigned long long end16[kMaxPeers];  // running end of job q in 16-byte units (prefix sum)
+  int n;
+};
+__global__ void __launch_bounds__(256) pj_sm_copy_jobs_kernel(PjCopyJobs jobs) {
+  const unsigned long long total = jobs.n ? jobs.end16[jobs.n - 1] : 0;
+  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int q = 0;
+    while (i >= jobs.end16[q]) ++q;
+    const unsigned long long at = i - (q ? jobs.end16[q - 1] : 0ull);
+    jobs.dst[q][at] = __ldg(jobs.src[q] + at);
+  }
+}
+
 __global__ void pj_close_kernel(cc_probe_result *res, size_t cap, int *region_flag, int *err) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     res->overflow = (res->n_matches > cap ? 1 : 0) | (*region_flag ? 2 : 0) | (*err ? 4 : 0);
@@ -214,6 +233,14 @@ struct cc_pjoin {
   int n_slots = 1;                             // send slots (= pieces: the partition pass of a batch never waits for its copies)
   int n_cs = 4;                                // copy streams in use
   int n_direct = 0;                            // remote owners whose regions the scatter kernel stores straight into their arena
+  int sm_pct = 0;                              // per cent of every block copy that an SM kernel moves behind the partition pass (see create)
+  struct Deferred {                            // pieces whose signal waits for the SM copy at the end of cc_pjoin_probe_begin
+    int arena, piece, S, slot;
+    unsigned long long epoch;
+  };
+  std::vector<Deferred> deferred;
+  std::vector<PjCopyJobs> sm_jobs;             // one job list per piece of the batch being begun
+  cudaEvent_t sm_done = nullptr;
   int64_t *send[2 * kPjMaxPieces] = {};        // [owner][slice][cap]
   unsigned long long *d_counts = nullptr;      // [n_slots][P * Sa] fill counts of the scatter
   int *d_flag = nullptr, *d_err = nullptr;     // sticky region-overrun flag, wait-timeout flag
@@ -319,7 +346,7 @@ int signal_consumed(cc_pjoin *j, int arena, unsigned long long epoch, cudaStream
 // first_of_use: the arena is about to be refilled for the first time in this use -- wait until every owner has consumed its
 // previous use.
 int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, int arena, int piece, unsigned long long epoch, bool first_of_use,
-               cudaStream_t st) {
+               cudaStream_t st, bool sm_share = false) {
   const int P = j->world;
   const PjLayout &lay = j->lay;
   const unsigned long long k = j->sends++;
@@ -364,17 +391,35 @@ int send_piece(cc_pjoin *j, const int64_t *d_keys, size_t n, int S, int log2s, i
   const int chunks = (dests == 0 || dests >= j->n_cs) ? 1 : (j->n_cs + dests - 1) / dests;
   const size_t chunk_rows = ((rows + chunks - 1) / chunks + 511) / 512 * 512;
   int n_copy = 0;
+  // sm_share: the last rows_sm rows of every block are left to an SM copy kernel that cc_pjoin_probe_begin launches behind the
+  // partition pass of the whole batch -- in the steady state of a copy-bound step the SMs would otherwise idle there, waiting
+  // for the copy engines (which run at half their idle rate under the kernels)
+  const size_t rows_sm = (sm_share && in_place) ? ((rows * (size_t) j->sm_pct / 100) / 512 * 512) : 0;
+  const size_t rows_ce = rows - rows_sm;
+  PjCopyJobs jobs;
+  jobs.n = 0;
   for (int i = 0; i < P; ++i) {
     const int o = (j->rank + i) % P;  // stagger the destinations so that the ranks do not all hit the same peer at once
     if (direct[o]) continue;          // written in place by the scatter kernel
     int64_t *dst = j->arena(o, arena) + lay.region_index(piece, j->rank, 0) * lay.cap;
     const int64_t *src = j->send[slot] + (size_t) o * rows;
-    for (size_t at = 0; at < rows; at += chunk_rows)
-      PJ_CUDA(cudaMemcpyAsync(dst + at, src + at, std::min(chunk_rows, rows - at) * 8, cudaMemcpyDeviceToDevice, j->cs[n_copy++ % j->n_cs]));
+    for (size_t at = 0; at < rows_ce; at += chunk_rows)
+      PJ_CUDA(cudaMemcpyAsync(dst + at, src + at, std::min(chunk_rows, rows_ce - at) * 8, cudaMemcpyDeviceToDevice, j->cs[n_copy++ % j->n_cs]));
+    if (rows_sm) {
+      jobs.dst[jobs.n] = reinterpret_cast<uint4 *>(dst + rows_ce);
+      jobs.src[jobs.n] = reinterpret_cast<const uint4 *>(src + rows_ce);
+      jobs.end16[jobs.n] = (jobs.n ? jobs.end16[jobs.n - 1] : 0ull) + rows_sm / 2;
+      ++jobs.n;
+    }
   }
   for (int s = 1; s < j->n_cs; ++s) {
     PJ_CUDA(cudaEventRecord(j->joined[s], j->cs[s]));
     PJ_CUDA(cudaStreamWaitEvent(c0, j->joined[s], 0));
+  }
+  if (rows_sm) {  // signalled by cc_pjoin_probe_begin once the SM copy has run
+    j->sm_jobs.push_back(jobs);
+    j->deferred.push_back({arena, piece, S, slot, epoch});
+    return CC_OK;
   }
   CC_TRY(signal_piece(j, arena, piece, S, counts, epoch, c0));
   PJ_CUDA(cudaEventRecord(j->copied[slot], c0));
@@ -400,6 +445,7 @@ void pj_release(cc_pjoin *j) {
   for (auto &e : j->joined)
     if (e) cudaEventDestroy(e);
   if (j->gate) cudaEventDestroy(j->gate);
+  if (j->sm_done) cudaEventDestroy(j->sm_done);
   if (j->table) cc_ht_destroy(j->table);
   delete j;
 }
@@ -500,6 +546,8 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   };
   j->n_cs = env_int("CCB_PJ_COPY_STREAMS", 4, 1, kPjMaxCopyStreams);      // measurement switches, see DESIGN.md
   j->n_direct = env_int("CCB_PJ_DIRECT", 0, 0, P - 1);                    // remote owners served by the scatter kernel's own NVLink stores
+  // share of every block copy that an SM kernel moves: 0 unless the step is copy-bound (many ranks: 7/8 of the keys travel)
+  j->sm_pct = env_int("CCB_PJ_SM_COPY_PCT", 0, 0, 90);
   for (int b = 0; b < j->n_slots && e == cudaSuccess; ++b) e = cudaMalloc(&j->send[b], (size_t) P * S * lay.cap * 8);
   if (e == cudaSuccess) e = cudaMalloc(&j->d_counts, (size_t) j->n_slots * P * S * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&j->d_flag, sizeof(int));
@@ -513,6 +561,7 @@ int cc_pjoin_create(cc_pjoin **out, const cc_comm *comm, int kind, const int64_t
   }
   for (int i = 0; i < j->n_cs && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&j->joined[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->gate, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->sm_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     set_error("cc_pjoin_create: %s (exchange memory: %zu bytes)", cudaGetErrorString(e), lay.total);
@@ -680,8 +729,27 @@ int cc_pjoin_probe_begin(cc_pjoin *j, const int64_t *d_keys, size_t n, cc_stream
   const size_t per = (n + B - 1) / B;
   for (int b = 0; b < B; ++b) {
     const size_t off = std::min(n, (size_t) b * per), cnt = std::min(per, n - off);
-    CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, j->slices, j->log2s, arena, b, epoch, b == 0, st));
+    CC_TRY(send_piece(j, cnt ? d_keys + off : nullptr, cnt, j->slices, j->log2s, arena, b, epoch, b == 0, st, j->sm_pct > 0));
     pj_mark(j, st, "F", b);
+  }
+  if (!j->deferred.empty()) {
+    // the SM share of the block copies, behind the partition pass of the whole batch; then the pieces are signalled
+    // (the kernel stores into the owners' arenas: they must have consumed the arena's previous use -- long ago in steady state)
+    if (epoch > 1) CC_TRY(wait_flags(j, consumed_flag(j, j->rank, arena, 0), j->world, epoch - 1, st));
+    for (const PjCopyJobs &jobs : j->sm_jobs) {
+      pj_sm_copy_jobs_kernel<<<sm_count() * 4, 256, 0, st>>>(jobs);
+      CC_CHECK_LAUNCH();
+    }
+    pj_mark(j, st, "SMCOPY");
+    PJ_CUDA(cudaEventRecord(j->sm_done, st));
+    cudaStream_t c0 = j->cs[0];
+    PJ_CUDA(cudaStreamWaitEvent(c0, j->sm_done, 0));
+    for (const cc_pjoin::Deferred &d : j->deferred) {
+      CC_TRY(signal_piece(j, d.arena, d.piece, d.S, j->d_counts + (size_t) d.slot * j->world * j->lay.Sa, d.epoch, c0));
+      PJ_CUDA(cudaEventRecord(j->copied[d.slot], c0));
+    }
+    j->deferred.clear();
+    j->sm_jobs.clear();
   }
   j->begun.push_back({arena, epoch, j->calls++});
   return CC_OK;
