@@ -51,6 +51,8 @@ def test_cpp_pjoin_driver_matches_oracle(ccb, tmp_path, world, table, cf, hit):
     env = dict(os.environ)
     if cf != 8:
         env["CCB_PJ_SLICE_BYTES"] = str(32 << 10)
+    else:
+        env["CCB_PJ_SM_COPY_PCT"] = "25"  # a quarter of every block copy is moved by the SM copy kernel behind the partition pass
     out = subprocess.run([PJOIN, "--gpus", str(world), "--log2-build", str(lb), "--log2-probe", str(lp), "--table", table, "--chunk-factor", str(cf),
                           "--hit", str(hit), "--steps", "2", "--sub-batches", "5", "--pipeline", "1" if table == "chain" else "0", "--dump", prefix],
                          capture_output=True, text=True, timeout=600, env=env)
