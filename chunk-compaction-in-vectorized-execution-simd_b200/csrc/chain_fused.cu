@@ -346,29 +346,38 @@ struct WarpShared {
   unsigned long long level_in[CC_MAX_JOINS], steps[CC_MAX_JOINS], lanes[CC_MAX_JOINS];
   uint32_t bufcnt[CC_MAX_JOINS + 1];
   uint32_t active[CC_MAX_JOINS];
+};
+// optional tail of a warp's slice (only when telemetry is requested: shared memory is what limits the resident warps)
+struct WarpHist {
   uint32_t hist[2][CC_MAX_JOINS][CC_DENSITY_BINS];  // [0]: rows handed to a Probe, [1]: live lanes of a Next round, as a fraction of W
 };
 
 constexpr int kWarpsPerCta = 4;  // independent pipeline instances per CTA (a CTA is only a container: 32 CTAs per SM would cap the warps)
-__host__ __device__ constexpr size_t chain_warp_smem(int n_joins, int W) {
-  return (sizeof(WarpShared) + (size_t) n_joins * 3 * (2 * W) * sizeof(uint32_t) + (size_t) (n_joins - 1) * (4 * W) * sizeof(uint32_t) + 15) & ~(size_t) 15;
+constexpr int kChunkMul = 3;  // chunk[L] holds kChunkMul * W row ids: fewer than W waiting + what a round may add (rounds emit only what fits)
+__host__ __device__ constexpr size_t chain_warp_smem(int n_joins, int W, bool telemetry) {
+  return (sizeof(WarpShared) + (size_t) n_joins * 3 * (2 * W) * sizeof(uint32_t) + (size_t) (n_joins - 1) * (kChunkMul * W) * sizeof(uint32_t) +
+          (telemetry ? sizeof(WarpHist) : 0) + 15) & ~(size_t) 15;
 }
 
+#ifndef CCB_CHAIN_MINB_R2
+#define CCB_CHAIN_MINB_R2 6  // resident CTAs per SM the compiler must allow for R = 2 (A/B: tools/build_variant.sh -DCCB_CHAIN_MINB_R2=8)
+#endif
 template <int R>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 : 3)) chain_warp_kernel(ChainArgs a) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? CCB_CHAIN_MINB_R2 : 3)) chain_warp_kernel(ChainArgs a) {
   static_assert(R >= 1 && R <= 4, "the match ranks of a round are packed into four 16-bit fields");
   constexpr int W = 32 * R;       // rows per chunk of this pipeline instance
   constexpr int SC = 2 * W;       // scan[L]: a probe step may add W lanes to W - 1 waiting ones
-  constexpr int BC = 4 * W;       // chunk[L]: a round emits only the matches that fit, the other lanes wait (see `room`)
+  constexpr int BC = kChunkMul * W;  // chunk[L]: a round emits only the matches that fit, the other lanes wait (see `room`)
   constexpr int KSC = 8;          // chain entries inspected per lane and round (two sectors: a 5-entry chain ends in one round)
   constexpr int KSL = 4;          // LP slots inspected per lane and round
   extern __shared__ __align__(16) unsigned char smem_all[];
-  unsigned char *smem_raw = smem_all + (threadIdx.x >> 5) * chain_warp_smem(a.n_joins, W);  // this warp's private slice
+  unsigned char *smem_raw = smem_all + (threadIdx.x >> 5) * chain_warp_smem(a.n_joins, W, a.tel != nullptr);  // this warp's private slice
   WarpShared &S = *reinterpret_cast<WarpShared *>(smem_raw);
   uint32_t *sc_row = reinterpret_cast<uint32_t *>(smem_raw + sizeof(WarpShared));  // [J][SC]
   uint32_t *sc_pos = sc_row + a.n_joins * SC;
   uint32_t *sc_end = sc_pos + a.n_joins * SC;
   uint32_t *bufs = sc_end + a.n_joins * SC;  // chunk[L] for L = 1 .. J-1 at bufs + (L-1)*BC
+  WarpHist *H = a.tel ? reinterpret_cast<WarpHist *>(bufs + (a.n_joins - 1) * BC) : nullptr;
   const int J = a.n_joins;
   const unsigned lane = threadIdx.x & 31u, lt = lanemask_lt();
   const auto need_of = [&](int l) -> uint32_t {  // threshold of the compactor behind join l, on this instance's chunk width
@@ -379,9 +388,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
   if (lane == 0) {
     for (int j = 0; j < CC_MAX_JOINS; ++j) S.level_in[j] = S.steps[j] = S.lanes[j] = 0, S.active[j] = 0;
     for (int j = 0; j <= CC_MAX_JOINS; ++j) S.bufcnt[j] = 0;
-    for (int k = 0; k < 2; ++k)
-      for (int j = 0; j < CC_MAX_JOINS; ++j)
-        for (int q = 0; q < CC_DENSITY_BINS; ++q) S.hist[k][j][q] = 0;
+    if (H)
+      for (int k = 0; k < 2; ++k)
+        for (int j = 0; j < CC_MAX_JOINS; ++j)
+          for (int q = 0; q < CC_DENSITY_BINS; ++q) H->hist[k][j][q] = 0;
     atomicMax((unsigned long long *) &a.res->reserved[1], ~(unsigned long long) globaltimer_ns());  // ~(earliest start): 0-initialised
   }
   __syncwarp();
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
         // The next level's chunk takes what fits.  Ranks grow with the entry index, so the entries that fit are a prefix; an
         // entry beyond it is put back as it was (position restored, still waiting) and emits nothing in this round.  At least
         // one entry always fits: the chunk holds fewer than W rows here (else the state machine had descended) and an entry
-        // emits at most KSC <= BC - W matches.
+        // emits at most KSC <= BC - W matches (BC = 3 W >= 96).
         const uint32_t room = (uint32_t) BC - S.bufcnt[L + 1];
         if (total > room) {
           uint32_t fit_end = 0;
@@ -581,7 +591,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
         S.active[L] = sbase;
         S.steps[L] += 1;
         S.lanes[L] += (unsigned long long) lanes;
-        S.hist[1][L][bin_of(lanes)] += 1;
+        if (H) H->hist[1][L][bin_of(lanes)] += 1;
       }
       __syncwarp();
       continue;
@@ -662,7 +672,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
       if (lane == 0) {
         S.active[L] = base;
         S.level_in[L] += (unsigned long long) n_valid;
-        S.hist[0][L][bin_of(n_valid)] += 1;
+        if (H) H->hist[0][L][bin_of(n_valid)] += 1;
       }
       __syncwarp();
       continue;
@@ -709,7 +719,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
   if (a.tel) {  // one atomic per non-empty (histogram, level, bin) and warp, lanes share the bins
     for (int idx = (int) lane; idx < 2 * J * CC_DENSITY_BINS; idx += 32) {
       const int k = idx / (J * CC_DENSITY_BINS), j = (idx / CC_DENSITY_BINS) % J, q = idx % CC_DENSITY_BINS;
-      const uint32_t v = S.hist[k][j][q];
+      const uint32_t v = H->hist[k][j][q];
       if (v) atomicAdd((unsigned long long *) (k == 0 ? &a.tel->probe_rows_hist[j][q] : &a.tel->round_lanes_hist[j][q]), (unsigned long long) v);
     }
   }
@@ -718,7 +728,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, R == 1 ? 10 : (R == 2 ? 6 :
 template <int R>
 static int launch_chain_warp(const ChainArgs &a, size_t n_joins, cudaStream_t st) {
   constexpr int W = 32 * R;
-  const size_t smem = chain_warp_smem((int) n_joins, W) * kWarpsPerCta;
+  const size_t smem = chain_warp_smem((int) n_joins, W, a.tel != nullptr) * kWarpsPerCta;
   CC_CUDA(cudaFuncSetAttribute(chain_warp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int per_sm = 0;
   CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_warp_kernel<R>, 32 * kWarpsPerCta, smem));

@@ -497,22 +497,24 @@ def test_chain_execute_materialized_tuples(ccb):
 
 
 def test_chain_execute_compaction_densifies(ccb):
-    """Full compaction must need far fewer probe steps than no compaction on a sparse chain."""
-    J, cf, rhs, rows = 4, 8, 20000, 300000
-    lhs = O.gen_lhs_main(rows, J, rhs)
+    """Full compaction must need clearly fewer rounds, with clearly more live lanes each, than no compaction on a sparse chain
+    (SURVEY 10).  The golden LHS is repeated 30 times so that every pipeline instance gets dozens of chunks: with less than one
+    chunk per instance (300 000 rows over ~3500 instances) the run is one long flush of half-filled caches under any threshold."""
+    J, cf, rhs, rows, reps = 4, 8, 20000, 300000, 30
+    lhs = np.tile(O.gen_lhs_main(rows, J, rhs), (reps, 1))
     cols = [dev(lhs[:, j].copy()) for j in range(J)]
     tables = [ccb.HashTable(rhs, cf) for _ in range(J)]
     full = ccb.chain_execute(tables, cols)
     none = ccb.chain_execute(tables, cols, thresholds=[0] * J)
-    assert (full["n_tuples"], full["digest"]) == (none["n_tuples"], none["digest"]) == (270336, 10954991527034855424)
+    want = (270336 * reps, (10954991527034855424 * reps) % (1 << 64))  # count and digest are sums over the result tuples
+    assert (full["n_tuples"], full["digest"]) == (none["n_tuples"], none["digest"]) == want
     # A round of the fused kernel inspects a whole sector or two of a lane's chain and emits ALL of its matches at once (the GPU
     # form of InOneNext), so even without compaction a level hands down denser chunks than the reference's one-match-per-Next
-    # protocol; what the threshold controls is how many lanes a round runs with.  Over all levels: clearly fewer rounds and
-    # clearly more live lanes per round with full compaction.
-    assert sum(full["level_steps"]) * 1.3 < sum(none["level_steps"]), (full["level_steps"], none["level_steps"])
+    # protocol; what the threshold controls is how many lanes a round runs with.
+    assert sum(full["level_steps"]) * 1.5 < sum(none["level_steps"]), (full["level_steps"], none["level_steps"])
     dens_full = sum(full["level_lanes"]) / max(1, sum(full["level_steps"]))
     dens_none = sum(none["level_lanes"]) / max(1, sum(none["level_steps"]))
-    assert dens_full > 1.3 * dens_none, (dens_full, dens_none)
+    assert dens_full > 1.5 * dens_none, (dens_full, dens_none)
 
 
 def test_chain_telemetry_histograms(ccb, tmp_path):
