@@ -269,7 +269,11 @@ int cc_probe_stream_finish(cc_probe_stream *h, cc_stream_t stream);
  *     and no row ids are requested; 1 always direct; 2 always partitioned; 3 always partitioned with the
  *     two-pass (histogram + scatter) partition instead of the default single-pass one.
  * slice_bytes: target table bytes per partition (0 keeps the current value, default 32 MiB).
- * The partitioned path needs n * 8 bytes of stream-ordered scratch (cudaMallocAsync).       */
+ * The partitioned path needs n * 8 bytes of stream-ordered scratch (cudaMallocAsync).
+ * THREADING: cc_probe_set_strategy / _cache_mode / _profiling and cc_partition_set_peer_blocks are PROCESS-WIDE measurement
+ * settings and cc_probe_last_phase_ms reads process-wide events: set them before the probes they should affect and do not
+ * change them while another thread probes.  Everything else is safe to call from several threads on different handles /
+ * streams (cc_probe_batch_host serialises on its workspace).                                                              */
 int cc_probe_set_strategy(int strategy, size_t slice_bytes);
 /* Cache behaviour of the probe kernel's memory operations (tuning knob; results never change):
  *   bit 0: reserved (128-byte L2 line prefetch of table loads: measured harmful, ignored)
