@@ -534,7 +534,14 @@ def main() -> int:
             line["roofline"] = {"bound": "hbm", "achieved": ALGO_BYTES_PER_TUPLE * n_probe / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": ALGO_BYTES_PER_TUPLE * n_probe / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None,
                                 "note": "per-GPU, whole step (partition + all-to-all + probe); NVLink moves 8 B x (N-1)/N per key each way",
-                                "peak_source": peak_src}
+                                "peak_source": peak_src,
+                                # the exchange against the NVLink roofline: bytes each GPU sends (= receives) per step
+                                "nvlink": {"bytes_per_gpu_per_step_each_way": 8 * n_probe * (world - 1) // world,
+                                           "achieved_GBps_each_way": 8 * n_probe * (world - 1) / world / (ms_per_step * 1e-3) / 1e9,
+                                           "peak_GBps_each_way": 900.0,
+                                           "frac": 8 * n_probe * (world - 1) / world / (ms_per_step * 1e-3) / 1e9 / 900.0,
+                                           "note": "nominal NVLink 5 rate per direction; measured on this pool: copy engines 660 GB/s on an idle GPU, "
+                                                   "280-375 GB/s while the partition / probe kernels run (profiles/r2_nvlink_bench_n2.txt, DESIGN.md section 6)"}}
 
     # ---- end to end through the host-buffer C-ABI call (H2D + probe + D2H inside the timed region)
     if not distributed:
